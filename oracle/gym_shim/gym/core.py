@@ -1,0 +1,26 @@
+class Env(object):
+    """Old-gym Env base: reset() -> obs, step(a) -> (obs, reward, done, info)."""
+    metadata = {"render.modes": []}
+    reward_range = (-float("inf"), float("inf"))
+    spec = None
+    action_space = None
+    observation_space = None
+
+    def step(self, action):
+        raise NotImplementedError
+
+    def reset(self):
+        raise NotImplementedError
+
+    def render(self, mode="human"):
+        raise NotImplementedError
+
+    def close(self):
+        pass
+
+    def seed(self, seed=None):
+        return
+
+    @property
+    def unwrapped(self):
+        return self
