@@ -1,0 +1,183 @@
+// scg_bg.cu -- beergame-v0 / beergame-v2 kernels (all-integer dynamics, one thread = one env).
+//
+// Restated from the reference (paths relative to its repo root):
+//   gym_supplychain/envs/beergame_env.py:66-138    BeerGameEnv.step   (action = delta on incoming order)
+//   gym_supplychain/envs/beergame_env.py:140-156   reset
+//   gym_supplychain/envs/beergame2_env.py:114-192  BeerGameEnv2.step  (action = order; capacity penalty)
+//   gym_supplychain/envs/beergame2_env.py:79-109   reset, randint demand / delays
+// The reference's table of shipments indexed by absolute week becomes a ring of `ring` slots
+// (slot k = what arrives in week+1+k), shifted once per week, so the state is a few dozen int32
+// that stay in registers for the whole rollout.  With 4 levels an action/obs row is 16 bytes:
+// every lane moves its row with one 128-bit access and a warp touches 512 contiguous bytes.
+#include "scg_internal.h"
+
+namespace scg {
+
+template <int LMAX, int RMAX, bool STATIC>
+__global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
+                                                 const int32_t* __restrict__ inj_delays, RngKey key, long long first_env,
+                                                 int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
+                                                 int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
+                                                 int32_t* __restrict__ reward, unsigned char* __restrict__ done) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = st.n;
+    const int L = STATIC ? LMAX : sp.L;
+    const int RING = STATIC ? RMAX : sp.ring;
+    ReturnStats rs; rs.init();
+    if (env < n) {
+        int inv[LMAX], back[LMAX], placed[LMAX], tr[RMAX][LMAX];
+        int week = st.week[env];
+        unsigned episode = (unsigned)st.episode[env];
+        double ep_ret = st.ep_ret[env];
+        const unsigned long long genv = (unsigned long long)(first_env + env);
+
+        auto do_reset_state = [&]() {                                  // beergame_env.py:140-148
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) {
+                inv[i] = sp.inv0[i]; back[i] = 0; placed[i] = sp.init_orders;
+#pragma unroll
+                for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] = (k < 2) ? sp.init_ship : 0;   // weeks 1..2 (:52)
+            }
+        };
+        if (do_reset && (reset_mask == nullptr || reset_mask[env])) {
+            ++episode; week = 0; ep_ret = 0.0;
+            do_reset_state();
+        } else {
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) {
+                inv[i] = st.inv[(long long)i * n + env];
+                back[i] = st.backlog[(long long)i * n + env];
+                placed[i] = st.placed[(long long)i * n + env];
+#pragma unroll
+                for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] = st.transit[((long long)k * L + i) * n + env];
+            }
+        }
+        const int off = sp.version == 2 ? sp.max_stock : 0;            // beergame2_env.py:111-112
+        auto write_obs = [&](long long io) {
+            if (obs == nullptr) return;
+            if (STATIC && LMAX == 4) {
+                int4 o = make_int4(off + inv[0] - back[0], off + inv[1] - back[1], off + inv[2] - back[2], off + inv[3] - back[3]);
+                reinterpret_cast<int4*>(obs)[io] = o;
+            } else {
+                for (int i = 0; i < L; ++i) obs[io * L + i] = off + inv[i] - back[i];
+            }
+        };
+        if (n_steps == 0) write_obs(env);
+        for (int s = 0; s < n_steps; ++s) {
+            const long long io = (long long)s * n + env;
+            if (week >= sp.T) {                                        // finished, not auto-reset: frozen
+                write_obs(io); reward[io] = 0; done[io] = 1;
+                continue;
+            }
+            int act[LMAX];
+            if (actions == nullptr) {                                  // random policy, keyed (env, episode, week)
+                Philox4 b0 = rng_block(key, genv, episode, (unsigned)(week + 1), STREAM_ACTION, 0);
+                Philox4 b1 = rng_block(key, genv, episode, (unsigned)(week + 1), STREAM_ACTION, 1);
+#pragma unroll
+                for (int i = 0; i < LMAX; ++i)
+                    if (i < L) act[i] = sp.version == 2 ? uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), 0, (unsigned)sp.max_order)
+                                                        : uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), -2, 7);
+            } else if (STATIC && LMAX == 4) {
+                const int4 a = reinterpret_cast<const int4*>(actions)[io];
+                act[0] = a.x; act[1] = a.y; act[2] = a.z; act[3] = a.w;
+            } else {
+                for (int i = 0; i < L; ++i) act[i] = actions[io * L + i];
+            }
+            ++week;
+            // 1. receive what is due this week and advance the ring (:67-72)
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) {
+                inv[i] += tr[0][i];
+#pragma unroll
+                for (int k = 0; k + 1 < RMAX; ++k) if (k + 1 < RING) tr[k][i] = tr[k + 1][i];
+                tr[RING - 1][i] = 0;
+            }
+            // customer demand and this week's delay
+            int dem, delay;
+            if (inj_demand) dem = inj_demand[(long long)(week - 1) * n + env];
+            else if (sp.dem_hi > sp.dem_lo)
+                dem = uniform_int(rng_block(key, genv, episode, (unsigned)(week - 1), STREAM_BG_DEMAND, 0).x, sp.dem_lo,
+                                  (unsigned)(sp.dem_hi - sp.dem_lo));                     // randint(lo, hi): hi exclusive
+            else dem = sp.demand[week - 1];
+            if (inj_delays) delay = inj_delays[(long long)(week - 1) * n + env];
+            else if (sp.del_hi > sp.del_lo)
+                delay = uniform_int(rng_block(key, genv, episode, (unsigned)week, STREAM_BG_DELAY, 0).x, sp.del_lo,
+                                    (unsigned)(sp.del_hi - sp.del_lo));
+            else delay = sp.delays[week - 1];
+            // 2. fill orders (:79-89)
+            int incoming[LMAX], fill[LMAX], deliver[LMAX];
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) {
+                incoming[i] = (i == 0) ? dem : placed[i - 1];
+                fill[i] = incoming[i] + back[i];
+                deliver[i] = min(inv[i], fill[i]);
+            }
+            // ship downstream; delay 0 lands in the lower level's inventory before its own decrement (:93-96)
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i + 1 < L) {
+                if (delay == 0) inv[i] += deliver[i + 1];
+                else {
+#pragma unroll
+                    for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] += (k == delay - 1) ? deliver[i + 1] : 0;
+                }
+            }
+            // 3. inventory / backlog (:101-103)
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) { inv[i] -= deliver[i]; back[i] = fill[i] - deliver[i]; }
+            // 4. the brewery's own order comes back after the delay (:111-114)
+            if (delay == 0) inv[L - 1] += placed[L - 1];
+            else {
+#pragma unroll
+                for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][L - 1] += (k == delay - 1) ? placed[L - 1] : 0;
+            }
+            // 5. place orders (beergame_env.py:121 / beergame2_env.py:168)
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) placed[i] = sp.version == 2 ? act[i] : incoming[i] + act[i];
+            // 6. reward (:130 / beergame2_env.py:177-180)
+            int r = 0;
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) if (i < L) {
+                r -= sp.inv_cost * inv[i] + sp.backlog_cost * back[i];
+                if (sp.version == 2) r -= sp.penalty * (max(inv[i] - sp.max_stock, 0) + max(back[i] - sp.max_stock, 0));
+            }
+            ep_ret += (double)r;
+            const bool fin = (week == sp.T);
+            if (fin) {
+                rs.add(ep_ret);
+                if (auto_reset) { ++episode; week = 0; ep_ret = 0.0; do_reset_state(); }
+            }
+            write_obs(io);
+            reward[io] = r;
+            done[io] = fin ? 1 : 0;
+        }
+        st.week[env] = week; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) if (i < L) {
+            st.inv[(long long)i * n + env] = inv[i];
+            st.backlog[(long long)i * n + env] = back[i];
+            st.placed[(long long)i * n + env] = placed[i];
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k) if (k < RING) st.transit[((long long)k * L + i) * n + env] = tr[k][i];
+        }
+    }
+    rs.flush(st.stats);
+}
+
+int bg_run(const BgRun& r) {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((r.st.n + threads - 1) / threads);
+    const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
+    const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
+#define SCG_BG_LAUNCH(LM, RM, ST)                                                                              \
+    bg_kernel<LM, RM, ST><<<blocks, threads, 0, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,      \
+                                                            r.first_env, r.auto_reset, n_steps, r.reset_mask,   \
+                                                            do_reset, r.actions, r.obs, r.reward, r.done)
+    if (r.sp.L == 4 && r.sp.ring == 2) SCG_BG_LAUNCH(4, 2, true);
+    else if (r.sp.L == 4 && r.sp.ring == 4) SCG_BG_LAUNCH(4, 4, true);
+    else SCG_BG_LAUNCH(8, 8, false);
+#undef SCG_BG_LAUNCH
+    SCG_CUDA(cudaGetLastError());
+    return SCG_OK;
+}
+
+}  // namespace scg

@@ -1,0 +1,610 @@
+// scg_sc_device.cuh -- device-side SupplyChainEnv dynamics (one thread = one env).
+//
+// One templated node-step (`sc_step_nodes`) serves every kernel; three policies vary:
+//   Topo  : where topology and per-node constants come from
+//             DynTopo      runtime CSR + arrays in global memory (any nodes_info DAG)
+//             LayeredTopo  compile-time S-F-W-R full-bipartite chain, constants in the kernel
+//                          parameter bank (scg_sc_static.cuh) -> loops unroll, state in registers
+//   Pipe  : how stock and in-transit material are stored
+//             RingGlobal   pre-summed lead-time ring in global memory   (FAST modes, generic)
+//             RingRegs     pre-summed lead-time ring in registers       (FAST modes, static)
+//             HeapGlobal   CPython-heapq-exact queues of (time, amount) (EXACT mode)
+//   Real  : float or double.
+//
+// Semantics restated from the reference (paths relative to its repo root):
+//   supplychain_env.py:49-96    SC_Action.apply (SUPPLY scaling, SHIP sorted cuts)
+//   supplychain_env.py:208-396  SC_Node.act
+//   supplychain_env.py:402-412  SC_Node.reset
+//   supplychain_env.py:428-463  SC_Node.build_observation
+//   supplychain_env.py:697-748  step; :762-791 _build_observation
+// including its quirks.  The fp64 translation unit is compiled with
+// -fmad=false so every product and sum rounds exactly as numpy's does.
+#pragma once
+#include "scg_common.cuh"
+
+namespace scg {
+
+constexpr int SC_MAXD = 32;     // max destinations per node in the generic kernels
+constexpr int SC_MAXP = 8;      // max products
+
+// ---------------------------------------------------------------------------------
+// Device copy of the spec (arrays in global memory, typed in the handle's Real).
+// ---------------------------------------------------------------------------------
+template <class Real>
+struct ScDevSpec {
+    int N, P, E, T, avgL, maxL, stochL, RP, A, O, K, ring, heapcap, n_init;
+    Real c_unmet, c_xstock, c_xproc, c_xship;
+    const int* last;        // [N]
+    const int* ebeg;        // [N+1]
+    const int* act_off;     // [N] first action index of the node
+    const int* lt_off;      // [N] first lead-time index of the node (stochastic lead times)
+    const int* ret_idx;     // [N] retailer ordinal (or -1)
+    const int* is_sup;      // [N] node has at least one SUPPLY action
+    const Real* proc_cap;   // [N]
+    const Real *stock0, *cap, *hold, *sup_cap, *sup_cost, *ratio, *proc_cost, *max_ship;   // [N*P]
+    const int* edst;        // [E]
+    const Real* ecap;       // [E]
+    const Real* ecost;      // [E*P]
+    const int* ibeg;        // [N*P+1]
+    const int* itime;       // [n_init]
+    const Real* iamt;       // [n_init]
+    const int* dkind;       // [P]
+    const double *dlo, *dhi, *dstd, *dpeaks, *dminavg, *dmaxavg;   // [P]
+};
+
+// Per-launch inputs common to all kernels.
+struct ScInputs {
+    const int32_t* inj_demand;      // [T+1][RP][n] or nullptr
+    const int32_t* inj_leadtimes;   // [T][K][n] or nullptr
+    RngKey key;
+    long long first_env;
+    int auto_reset;
+};
+
+// Global env state, env-minor ("SoA"): element i of env e lives at base[i*n + e].
+template <class Real>
+struct ScState {
+    long long n;
+    int* t;            // [n] period of the current episode (0 after reset)
+    int* episode;      // [n] episode counter (Philox counter word)
+    double* ep_ret;    // [n] return accumulated so far in the episode
+    Real* stock;       // [N*P][n]
+    Real* slot;        // FAST:  [N*P*ring][n]  slot k = material arriving at t+1+k
+    int* hlen;         // EXACT: [N*P][n]
+    int* htime;        // EXACT: [N*P*heapcap][n]
+    double* hamt;      // EXACT: [N*P*heapcap][n]
+    double* stats;     // [5] count, sum, sumsq, min, max of finished-episode returns
+};
+
+// ---------------------------------------------------------------------------------
+// stochastic inputs
+// ---------------------------------------------------------------------------------
+template <class Real>
+__device__ __forceinline__ int sc_demand(const ScDevSpec<Real>& sp, const ScInputs& in, long long n_envs, long long env,
+                                         unsigned episode, int row, int rp, int p) {
+    if (in.inj_demand) return in.inj_demand[((long long)row * sp.RP + rp) * n_envs + env];
+    const unsigned long long genv = (unsigned long long)(in.first_env + env);
+    const int kind = sp.dkind[p];
+    const double lo = sp.dlo[p], hi = sp.dhi[p];
+    if (kind == 0) {
+        Philox4 b = rng_block(in.key, genv, episode, (unsigned)row, STREAM_DEMAND, (unsigned)(rp >> 2));
+        return uniform_int(pick_word(b, rp & 3), (int)lo, (unsigned)((int)hi - (int)lo + 1));
+    }
+    Philox4 b = rng_block(in.key, genv, episode, (unsigned)row, STREAM_DEMAND_NOISE, (unsigned)(rp >> 1));
+    const unsigned w0 = pick_word(b, 2 * (rp & 1)), w1 = pick_word(b, 2 * (rp & 1) + 1);
+    const double sd = sp.dstd[p];
+    double x;
+    if (kind == 1) {
+        x = (hi + lo) / 2 + sd * normal_from(w0, w1);                       // demands_generator.py:41
+    } else {
+        double base = sp.dminavg[p] + (sp.dmaxavg[p] - sp.dminavg[p]) / 2 *
+                      (1.0 + sin(sp.dpeaks[p] * 2.0 * 3.141592653589793 / (double)sp.T * (double)row));   // :72-82
+        double noise = (kind == 2) ? sd * normal_from(w0, w1)
+                                   : (double)uniform_int(w0, -3 * (int)sd, (unsigned)(6 * (int)sd + 1));  // :75-77
+        x = base + noise;
+    }
+    x = fmin(fmax(x, lo), hi);
+    return (int)rint(x);                                                    // np.rint: half-to-even
+}
+
+template <class Real>
+__device__ __forceinline__ int sc_leadtime(const ScDevSpec<Real>& sp, const ScInputs& in, long long n_envs, long long env,
+                                           unsigned episode, int t, int k) {
+    if (!sp.stochL) return sp.avgL;                                         // supplychain_env.py:724
+    if (in.inj_leadtimes) return in.inj_leadtimes[((long long)(t - 1) * sp.K + k) * n_envs + env];
+    const unsigned long long genv = (unsigned long long)(in.first_env + env);
+    Philox4 b = rng_block(in.key, genv, episode, (unsigned)t, STREAM_LEADTIME, (unsigned)(k >> 2));
+    return leadtime_from(pick_word(b, k & 3), (double)(sp.avgL - 1), sp.maxL);
+}
+
+// uniform action in [-1, 1) from one Philox word; the float value is what every mode sees
+__device__ __forceinline__ float action_from_word(unsigned w) { return (float)(int)w * 4.656612873077393e-10f; }
+
+// ---------------------------------------------------------------------------------
+// arithmetic helpers that differ between the exact fp64 path and the fp32 path
+// ---------------------------------------------------------------------------------
+template <class Real> __device__ __forceinline__ Real denorm_action(Real a);
+template <> __device__ __forceinline__ double denorm_action<double>(double a) { return (a + 1.0) / 2.0; }   // :697-698
+template <> __device__ __forceinline__ float denorm_action<float>(float a) { return fmaf(a, 0.5f, 0.5f); }
+
+template <class Real> __device__ __forceinline__ Real clamp_pm1(Real x) {
+    return x < (Real)-1 ? (Real)-1 : (x > (Real)1 ? (Real)1 : x);           // np.clip(.., -1, 1), :700-701
+}
+template <class Real> __device__ __forceinline__ Real obs_norm(Real x) { return clamp_pm1<Real>(x * (Real)2 - (Real)1); }
+
+// ---------------------------------------------------------------------------------
+// Topo policy: runtime topology
+// ---------------------------------------------------------------------------------
+template <class Real>
+struct DynTopo {
+    static constexpr bool kStatic = false;
+    static constexpr int kMaxD = SC_MAXD;
+    const ScDevSpec<Real>& sp;
+    __device__ __forceinline__ explicit DynTopo(const ScDevSpec<Real>& s) : sp(s) {}
+    __device__ __forceinline__ int N() const { return sp.N; }
+    __device__ __forceinline__ int P() const { return sp.P; }
+    __device__ __forceinline__ int avgL() const { return sp.avgL; }
+    __device__ __forceinline__ int maxL() const { return sp.maxL; }
+    __device__ __forceinline__ int ring() const { return sp.ring; }
+    __device__ __forceinline__ int T() const { return sp.T; }
+    __device__ __forceinline__ bool last(int n) const { return sp.last[n] != 0; }
+    __device__ __forceinline__ bool supplier(int n) const { return sp.is_sup[n] != 0; }
+    __device__ __forceinline__ int ebeg(int n) const { return sp.ebeg[n]; }
+    __device__ __forceinline__ int ndest(int n) const { return sp.ebeg[n + 1] - sp.ebeg[n]; }
+    __device__ __forceinline__ int edst(int e) const { return sp.edst[e]; }
+    __device__ __forceinline__ Real ecap(int e) const { return sp.ecap[e]; }
+    __device__ __forceinline__ Real ecost(int e, int p) const { return sp.ecost[e * sp.P + p]; }
+    __device__ __forceinline__ Real proc_cap(int n) const { return sp.proc_cap[n]; }
+    __device__ __forceinline__ Real cap(int n, int p) const { return sp.cap[n * sp.P + p]; }
+    __device__ __forceinline__ Real hold(int n, int p) const { return sp.hold[n * sp.P + p]; }
+    __device__ __forceinline__ Real sup_cap(int n, int p) const { return sp.sup_cap[n * sp.P + p]; }
+    __device__ __forceinline__ Real sup_cost(int n, int p) const { return sp.sup_cost[n * sp.P + p]; }
+    __device__ __forceinline__ Real ratio(int n, int p) const { return sp.ratio[n * sp.P + p]; }
+    __device__ __forceinline__ Real proc_cost(int n, int p) const { return sp.proc_cost[n * sp.P + p]; }
+    __device__ __forceinline__ Real max_ship(int n, int p) const { return sp.max_ship[n * sp.P + p]; }
+    __device__ __forceinline__ int act_off(int n) const { return sp.act_off[n]; }
+    __device__ __forceinline__ int lt_off(int n) const { return sp.lt_off[n]; }
+    __device__ __forceinline__ int ret_idx(int n) const { return sp.ret_idx[n]; }
+    __device__ __forceinline__ Real c_unmet() const { return sp.c_unmet; }
+    __device__ __forceinline__ Real c_xstock() const { return sp.c_xstock; }
+    __device__ __forceinline__ Real c_xproc() const { return sp.c_xproc; }
+    __device__ __forceinline__ Real c_xship() const { return sp.c_xship; }
+    __device__ __forceinline__ bool has_supply(int n, int p) const { return sup_cap(n, p) > (Real)0; }
+    __device__ __forceinline__ bool can_ship(int n, int p) const { return cap(n, p) > (Real)0 && ndest(n) > 0; }
+    __device__ __forceinline__ Real div_ratio(Real x, int n, int p) const { return x / ratio(n, p); }   // :310
+};
+
+// ---------------------------------------------------------------------------------
+// Pipe policies (global-memory flavours; the register flavour lives in scg_sc_static.cuh)
+// ---------------------------------------------------------------------------------
+template <class Real>
+struct RingGlobal {
+    static constexpr bool kTwoPhase = true;    // all arrivals first, then all node actions
+    static constexpr bool kExactObs = false;
+    Real* stock; Real* slot; long long n; int ring;
+    __device__ __forceinline__ RingGlobal(const ScState<Real>& st, long long env, int ring_)
+        : stock(st.stock + env), slot(st.slot + env), n(st.n), ring(ring_) {}
+    __device__ __forceinline__ Real get_stock(int np) const { return stock[(long long)np * n]; }
+    __device__ __forceinline__ void set_stock(int np, Real v) { stock[(long long)np * n] = v; }
+    __device__ __forceinline__ Real slot_at(int np, int k) const { return slot[((long long)np * ring + k) * n]; }
+    // material arriving now (slot 0), and shift the ring by one period
+    __device__ __forceinline__ Real arrive(int np, int /*t*/) {
+        Real* s = slot + (long long)np * ring * n;
+        Real a = s[0];
+        for (int k = 0; k + 1 < ring; ++k) s[(long long)k * n] = s[(long long)(k + 1) * n];
+        s[(long long)(ring - 1) * n] = (Real)0;
+        return a;
+    }
+    __device__ __forceinline__ void push(int np, int /*t*/, int lt, Real amount) {
+        slot[((long long)np * ring + (lt - 1)) * n] += amount;
+    }
+    template <class Tp>
+    __device__ __forceinline__ void reset(const Tp& tp, const ScDevSpec<Real>& sp) {
+        const int NP = sp.N * sp.P;
+        for (int np = 0; np < NP; ++np) {
+            set_stock(np, sp.stock0[np]);
+            for (int k = 0; k < ring; ++k) slot[((long long)np * ring + k) * n] = (Real)0;
+            for (int i = sp.ibeg[np]; i < sp.ibeg[np + 1]; ++i)
+                slot[((long long)np * ring + (sp.itime[i] - 1)) * n] += sp.iamt[i];
+        }
+    }
+};
+
+// EXACT: per (node, product) a binary heap of (time, amount) laid out exactly like CPython's
+// heapq list (Lib/heapq.py: heappush/_siftdown, heappop/_siftup), because the reference
+// observation reads that list by index (supplychain_env.py:445-461).
+struct HeapGlobal {
+    static constexpr bool kTwoPhase = false;   // reference order: node by node
+    static constexpr bool kExactObs = true;
+    double* stock; int* hlen; int* htime; double* hamt; long long n; int cap;
+    __device__ __forceinline__ HeapGlobal(const ScState<double>& st, long long env, int cap_)
+        : stock(st.stock + env), hlen(st.hlen + env), htime(st.htime + env), hamt(st.hamt + env), n(st.n), cap(cap_) {}
+    __device__ __forceinline__ double get_stock(int np) const { return stock[(long long)np * n]; }
+    __device__ __forceinline__ void set_stock(int np, double v) { stock[(long long)np * n] = v; }
+    __device__ __forceinline__ int& len(int np) { return hlen[(long long)np * n]; }
+    __device__ __forceinline__ int& tm(int np, int k) { return htime[((long long)np * cap + k) * n]; }
+    __device__ __forceinline__ double& am(int np, int k) { return hamt[((long long)np * cap + k) * n]; }
+    static __device__ __forceinline__ bool lt(int ta, double aa, int tb, double ab) {     // tuple '<'
+        return ta < tb || (ta == tb && aa < ab);
+    }
+    __device__ __forceinline__ void sift_down(int np, int start, int pos, int nt, double na) {
+        while (pos > start) {
+            int par = (pos - 1) >> 1;
+            int pt = tm(np, par); double pa = am(np, par);
+            if (lt(nt, na, pt, pa)) { tm(np, pos) = pt; am(np, pos) = pa; pos = par; } else break;
+        }
+        tm(np, pos) = nt; am(np, pos) = na;
+    }
+    __device__ __forceinline__ void push_item(int np, int when, double amount) {
+        int L = len(np);
+        if (L >= cap) return;                  // cannot happen: cap = n_src*maxL + n_init (host-checked)
+        len(np) = L + 1;
+        sift_down(np, 0, L, when, amount);
+    }
+    __device__ __forceinline__ double pop_item(int np) {
+        int L = len(np) - 1;
+        len(np) = L;
+        int lt_t = tm(np, L); double lt_a = am(np, L);
+        if (L == 0) return lt_a;
+        double ret = am(np, 0);
+        // _siftup(heap, 0) with newitem = last element
+        int pos = 0, child = 1;
+        while (child < L) {
+            int right = child + 1;
+            if (right < L && !lt(tm(np, child), am(np, child), tm(np, right), am(np, right))) child = right;
+            tm(np, pos) = tm(np, child); am(np, pos) = am(np, child);
+            pos = child; child = 2 * pos + 1;
+        }
+        sift_down(np, 0, pos, lt_t, lt_a);
+        return ret;
+    }
+    __device__ __forceinline__ double arrive(int np, int t) {                              // :220-225
+        double got = 0.0;
+        while (len(np) > 0 && tm(np, 0) == t) got += pop_item(np);
+        return got;
+    }
+    __device__ __forceinline__ void push(int np, int t, int lt_, double amount) { push_item(np, t + lt_, amount); }
+    template <class Tp>
+    __device__ __forceinline__ void reset(const Tp& tp, const ScDevSpec<double>& sp) {     // :402-412
+        const int NP = sp.N * sp.P;
+        for (int np = 0; np < NP; ++np) {
+            set_stock(np, sp.stock0[np]);
+            len(np) = 0;
+            for (int i = sp.ibeg[np]; i < sp.ibeg[np + 1]; ++i) push_item(np, sp.itime[i], sp.iamt[i]);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// SHIP action scaling (supplychain_env.py:58-96): destinations sorted by (action value, index);
+// each gets the slice of `limit` between consecutive cut points, never more than what is left.
+// ---------------------------------------------------------------------------------
+template <class Real, int MAXD>
+__device__ __forceinline__ void ship_cuts_dyn(const Real* v, int D, Real limit, Real* out) {
+    int order[MAXD];
+    for (int i = 0; i < D; ++i) {            // stable insertion sort on (value, index)
+        int j = i;
+        while (j > 0 && v[order[j - 1]] > v[i]) { order[j] = order[j - 1]; --j; }
+        order[j] = i;
+    }
+    Real left = limit, prev = (Real)0;
+    for (int k = 0; k < D; ++k) {
+        int i = order[k];
+        Real amount = (v[i] - prev) * limit;
+        if (amount > left) amount = left;
+        out[i] = amount;
+        left -= amount;
+        prev = v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// One period for all nodes of one env.  Returns the total cost (reward = -cost).
+//   Ar: action reader  Real get(int idx)   (raw action in [-1,1])
+//   Lr: lead-time reader  int get(int k)
+//   Dr: demand reader  int cur(int rp, int p)   (row t-1)
+// ---------------------------------------------------------------------------------
+template <class Real, class Tp, class Pp, class Ar, class Lr, class Dr>
+__device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& ar, Lr& lr, Dr& dr) {
+    constexpr int MAXD = Tp::kMaxD;
+    const int N = tp.N(), P = tp.P();
+    if (Pp::kTwoPhase) {
+#pragma unroll(Tp::kStatic ? 64 : 1)
+        for (int n = 0; n < N; ++n)
+#pragma unroll(Tp::kStatic ? 8 : 1)
+            for (int p = 0; p < P; ++p) {
+                const int np = n * P + p;
+                pp.set_stock(np, pp.get_stock(np) + pp.arrive(np, t));
+            }
+    }
+    Real total = (Real)0;
+#pragma unroll(Tp::kStatic ? 64 : 1)
+    for (int n = 0; n < N; ++n) {
+        Real cost = (Real)0;
+        // 1. arrivals (:220-228), 2. over-capacity: pay and discard (:232-240)
+#pragma unroll(Tp::kStatic ? 8 : 1)
+        for (int p = 0; p < P; ++p) {
+            const int np = n * P + p;
+            Real s = pp.get_stock(np);
+            if (!Pp::kTwoPhase) s = s + pp.arrive(np, t);
+            const Real c = tp.cap(n, p);
+            if (s > c) { cost += tp.c_xstock() * (s - c); s = c; }
+            pp.set_stock(np, s);
+        }
+        int ai = tp.act_off(n);
+        int li = tp.lt_off(n);
+        // 3. supply (:244-256); the lead-time cursor moves only when something was supplied (F4b)
+        if (tp.supplier(n)) {
+#pragma unroll(Tp::kStatic ? 8 : 1)
+            for (int p = 0; p < P; ++p) {
+                if (tp.has_supply(n, p)) {
+                    const Real amount = denorm_action<Real>(ar.get(ai)) * tp.sup_cap(n, p);
+                    ++ai;
+                    if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
+                    cost += amount * tp.sup_cost(n, p);
+                }
+            }
+        }
+        if (!tp.last(n)) {
+            // 4. ship (:262-375)
+            const int D = tp.ndest(n), e0 = tp.ebeg(n);
+            Real room[MAXD];
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+            for (int i = 0; i < D; ++i) room[i] = tp.ecap(e0 + i);
+            Real proc_left = tp.proc_cap(n);
+            const bool factory = proc_left > (Real)0;
+            const int base = li;
+#pragma unroll(Tp::kStatic ? 8 : 1)
+            for (int p = 0; p < P; ++p) {
+                const int np = n * P + p;
+                if (!tp.can_ship(n, p)) continue;                            // no SHIP action (:196-201)
+                Real over_ship = (Real)0, over_proc = (Real)0;
+                const Real s = pp.get_stock(np);
+                Real v[MAXD];
+                // (read unconditionally so the staged-row reader sees straight-line code)
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                for (int i = 0; i < D; ++i) v[i] = denorm_action<Real>(ar.get(ai + i));
+                if (s > (Real)0) {
+                    const Real c = tp.cap(n, p);
+                    const Real limit = c < s ? c : s;
+                    Real out[MAXD], send[MAXD];
+                    tp.ship_cuts(v, D, limit, out);
+                    const Real r = tp.ratio(n, p);
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                    for (int i = 0; i < D; ++i) send[i] = out[i];
+                    if (factory) {                                           // :298-310
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                        for (int i = 0; i < D; ++i) {
+                            if (out[i] > (Real)0) {
+                                if (out[i] > proc_left) { over_proc += out[i] - proc_left; out[i] = proc_left; }
+                                proc_left -= out[i];
+                            }
+                            send[i] = tp.div_ratio(out[i], n, p);
+                        }
+                    }
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                    for (int i = 0; i < D; ++i) {                            // :312-328 (F4a)
+                        if (send[i] > (Real)0 && send[i] > room[i]) {
+                            over_ship += send[i] - room[i];
+                            send[i] = room[i];
+                            out[i] = factory ? send[i] * r : send[i];
+                            room[i] -= out[i];
+                        }
+                    }
+                    Real leaving = (Real)0;
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                    for (int i = 0; i < D; ++i) leaving += out[i];           // :331
+                    pp.set_stock(np, s - leaving);
+                    if (factory) cost += leaving * tp.proc_cost(n, p);       // :338
+                    Real sc = (Real)0;
+#pragma unroll(Tp::kStatic ? MAXD : 1)
+                    for (int i = 0; i < D; ++i) {
+                        if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
+                        sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
+                    }
+                    cost += sc;
+                }
+                cost += tp.c_xproc() * over_proc;                            // :361
+                cost += tp.c_xship() * over_ship;                            // :366
+                ai += D;
+            }
+        } else {
+            // 5. retailers: serve what is possible, the rest is lost (:380-384)
+            const int r0 = tp.ret_idx(n) * P;
+#pragma unroll(Tp::kStatic ? 8 : 1)
+            for (int p = 0; p < P; ++p) {
+                const int np = n * P + p;
+                const Real d = (Real)dr.cur(r0 + p, p);
+                const Real s = pp.get_stock(np);
+                const Real served = s < d ? s : d;
+                pp.set_stock(np, s - served);
+                cost += tp.c_unmet() * (d - served);
+            }
+        }
+        // 6. holding cost (:390-391)
+#pragma unroll(Tp::kStatic ? 8 : 1)
+        for (int p = 0; p < P; ++p) cost += pp.get_stock(n * P + p) * tp.hold(n, p);
+        total += cost;
+    }
+    return total;
+}
+
+// Generic (runtime) helpers selected through the Topo policy.
+template <class Real>
+struct DynTopoOps : DynTopo<Real> {
+    __device__ __forceinline__ explicit DynTopoOps(const ScDevSpec<Real>& s) : DynTopo<Real>(s) {}
+    __device__ __forceinline__ void ship_cuts(const Real* v, int D, Real limit, Real* out) const {
+        ship_cuts_dyn<Real, SC_MAXD>(v, D, limit, out);
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// Observation (:428-463, :762-791).  Ow: void put(int idx, Real v).
+// ---------------------------------------------------------------------------------
+// FAST modes: canonical per-arrival-time sums out of the ring.
+template <class Real, class Tp, class Pp, class Dr, class Ow>
+__device__ __forceinline__ void sc_obs_ring(const Tp& tp, const ScDevSpec<Real>& sp, const Pp& pp, int t, Dr& dr, Ow& ow) {
+    const int N = tp.N(), P = tp.P(), L = tp.avgL(), ring = tp.ring();
+    int o = 0;
+    for (int rp = 0; rp < sp.RP; ++rp) {
+        const int p = rp % P;
+        const Real lo = (Real)sp.dlo[p], span = (Real)(sp.dhi[p] - sp.dlo[p]);
+        ow.put(o++, obs_norm<Real>(((Real)dr.next(rp, p) - lo) / span));
+    }
+    for (int n = 0; n < N; ++n) {
+        for (int p = 0; p < P; ++p) ow.put(o++, obs_norm<Real>(pp.get_stock(n * P + p) / tp.cap(n, p)));
+        for (int p = 0; p < P; ++p) {
+            const int np = n * P + p;
+            const Real ms = tp.max_ship(n, p);
+            for (int k = 0; k + 1 < L; ++k) ow.put(o++, obs_norm<Real>(pp.slot_at(np, k) / ms));
+            Real rest = (Real)0;
+            for (int k = L - 1; k < ring; ++k) rest += pp.slot_at(np, k);
+            ow.put(o++, obs_norm<Real>(rest / (ms * (Real)(tp.maxL() - (L - 1)))));
+        }
+    }
+    ow.put(o++, obs_norm<Real>((Real)(tp.T() - t) / (Real)tp.T()));
+}
+
+// EXACT mode: walk each heap ARRAY in index order exactly like the reference does.
+template <class Tp, class Dr, class Ow>
+__device__ __forceinline__ void sc_obs_heap(const Tp& tp, const ScDevSpec<double>& sp, HeapGlobal& pp, int t, Dr& dr, Ow& ow) {
+    const int N = tp.N(), P = tp.P(), L = tp.avgL();
+    int o = 0;
+    for (int rp = 0; rp < sp.RP; ++rp) {
+        const int p = rp % P;
+        ow.put(o++, obs_norm<double>(((double)dr.next(rp, p) - sp.dlo[p]) / (sp.dhi[p] - sp.dlo[p])));
+    }
+    for (int n = 0; n < N; ++n) {
+        for (int p = 0; p < P; ++p) ow.put(o++, obs_norm<double>(pp.get_stock(n * P + p) / tp.cap(n, p)));
+        for (int p = 0; p < P; ++p) {
+            const int np = n * P + p;
+            const int len = pp.len(np);
+            const double ms = tp.max_ship(n, p);
+            if (len == 0) { for (int k = 0; k < L; ++k) ow.put(o++, obs_norm<double>(0.0)); continue; }
+            int k = 0;
+            for (int when = t + 1; when < t + L; ++when) {
+                double s = 0.0;
+                while (k < len && pp.tm(np, k) == when) { s += pp.am(np, k); ++k; }
+                ow.put(o++, obs_norm<double>(s / ms));
+            }
+            double s = 0.0;
+            while (k < len) { s += pp.am(np, k); ++k; }
+            ow.put(o++, obs_norm<double>(s / (ms * (double)(tp.maxL() - (L - 1)))));
+        }
+    }
+    ow.put(o++, obs_norm<double>((double)(tp.T() - t) / (double)tp.T()));
+}
+
+// ---------------------------------------------------------------------------------
+// readers/writers used by the generic kernels
+// ---------------------------------------------------------------------------------
+template <class Real>
+struct GlobalActions {                 // actions[(step*n + env)*A + idx]  or Philox when null
+    const Real* row; bool random; RngKey key; unsigned long long genv; unsigned episode; int t;
+    Philox4 blk; int blk_id;
+    __device__ __forceinline__ Real get(int idx) {
+        if (!random) return row[idx];
+        const int b = idx >> 2;
+        if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
+        return (Real)action_from_word(pick_word(blk, idx & 3));
+    }
+};
+
+template <class Real>
+struct DynLeadtimes {
+    const ScDevSpec<Real>& sp; const ScInputs& in; long long n, env; unsigned episode; int t;
+    __device__ __forceinline__ int get(int k) const { return sc_leadtime(sp, in, n, env, episode, t, k); }
+};
+
+template <class Real>
+struct DynDemand {
+    const ScDevSpec<Real>& sp; const ScInputs& in; long long n, env; unsigned episode; int t;   // t = period just simulated
+    __device__ __forceinline__ int cur(int rp, int p) const { return sc_demand(sp, in, n, env, episode, t - 1, rp, p); }
+    __device__ __forceinline__ int next(int rp, int p) const { return sc_demand(sp, in, n, env, episode, t, rp, p); }
+};
+
+template <class Real>
+struct GlobalObs {
+    Real* row;
+    __device__ __forceinline__ void put(int idx, Real v) { if (row) row[idx] = v; }
+};
+
+// ---------------------------------------------------------------------------------
+// Generic kernels: any topology, state in global memory.
+//   MODE 0: FAST ring (Real = float|double);  MODE 1: EXACT heap (Real = double)
+// n_steps = 0 with a mask gives reset(); the same kernel serves step() (n_steps = 1).
+// ---------------------------------------------------------------------------------
+template <class Real, int MODE> struct PipeSel { using type = RingGlobal<Real>; };
+template <> struct PipeSel<double, 1> { using type = HeapGlobal; };
+
+template <class Real, int MODE>
+__device__ __forceinline__ typename PipeSel<Real, MODE>::type make_pipe(const ScState<Real>& st, long long env,
+                                                                        const ScDevSpec<Real>& sp) {
+    if constexpr (MODE == 1) return HeapGlobal(st, env, sp.heapcap);
+    else return RingGlobal<Real>(st, env, sp.ring);
+}
+
+template <class Real, int MODE, class Pp, class Dr, class Ow>
+__device__ __forceinline__ void sc_write_obs(const DynTopoOps<Real>& tp, const ScDevSpec<Real>& sp, Pp& pp, int t, Dr& dr, Ow& ow) {
+    if constexpr (MODE == 1) sc_obs_heap(tp, sp, pp, t, dr, ow);
+    else sc_obs_ring<Real>(tp, sp, pp, t, dr, ow);
+}
+
+template <class Real, int MODE>
+__global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
+                                                         const unsigned char* __restrict__ reset_mask, int do_reset,
+                                                         const Real* __restrict__ actions, Real* __restrict__ obs,
+                                                         Real* __restrict__ reward, unsigned char* __restrict__ done) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = env < st.n;
+    ReturnStats rs; rs.init();
+    if (active) {
+        DynTopoOps<Real> tp(sp);
+        auto pp = make_pipe<Real, MODE>(st, env, sp);
+        int t = st.t[env];
+        unsigned episode = (unsigned)st.episode[env];
+        double ep_ret = st.ep_ret[env];
+        if (do_reset && (reset_mask == nullptr || reset_mask[env])) {
+            ++episode; t = 0; ep_ret = 0.0;
+            pp.reset(tp, sp);
+        }
+        if (n_steps == 0) {       // reset(): emit the current observation
+            DynDemand<Real> dr{sp, in, st.n, env, episode, t};
+            GlobalObs<Real> ow{obs ? obs + env * sp.O : nullptr};
+            sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
+        }
+        for (int s = 0; s < n_steps; ++s) {
+            const long long io = (long long)s * st.n + env;
+            GlobalObs<Real> ow{obs ? obs + io * sp.O : nullptr};
+            if (t >= sp.T) {      // finished and not auto-reset: frozen
+                DynDemand<Real> dr{sp, in, st.n, env, episode, t};
+                sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
+                reward[io] = (Real)0; done[io] = 1;
+                continue;
+            }
+            ++t;
+            GlobalActions<Real> ar{actions ? actions + io * sp.A : nullptr, actions == nullptr, in.key,
+                                   (unsigned long long)(in.first_env + env), episode, t, Philox4{0, 0, 0, 0}, -1};
+            DynLeadtimes<Real> lr{sp, in, st.n, env, episode, t};
+            DynDemand<Real> dr{sp, in, st.n, env, episode, t};
+            const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr);
+            const Real r = -cost;
+            ep_ret += (double)r;
+            const bool fin = (t == sp.T);
+            if (fin) {
+                rs.add(ep_ret);
+                if (in.auto_reset) {
+                    ++episode; t = 0; ep_ret = 0.0;
+                    pp.reset(tp, sp);
+                    dr.episode = episode; dr.t = 0;
+                }
+            }
+            sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
+            reward[io] = r; done[io] = fin ? 1 : 0;
+        }
+        st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
+    }
+    rs.flush(st.stats);
+}
+
+}  // namespace scg

@@ -1,0 +1,42 @@
+// scg_sc_f32.cu -- fp32 instantiations of the supply-chain kernels (SCG_MODE_FAST_F32).
+// Compiled with the default FMA contraction: this is the throughput path; its results agree
+// with the reference to ~1e-7 relative per step (tests state the tolerance).
+#include "scg_sc_host.cuh"
+
+namespace scg {
+
+// static layered instantiations:  id -> (S, F, W, R, P, L)
+//   1: 1-1-1-1 P=1 L=2  (supplychain-linear-v0)
+//   2: 2-2-2-2 P=1 L=2  (supplychain-2perstage-v0 / sc-2perstage-v0)
+//   3: 3-3-3-3 P=2 L=2  (supplychain-ntom-v0 / sc-Nperstage-multiproduct-v0 defaults)
+//   4: 1-1-1-3 P=1 L=2  (supplychain-oneonen-v0)
+//   5: 2-2-2-2 P=2 L=2  (sc-2perstage-multiproduct-v0 defaults)
+int sc_match_variant_f32(const ScHostSpec& hs) {
+    if (sc_is_layered(hs, 1, 1, 1, 1, 1, 2)) return 1;
+    if (sc_is_layered(hs, 2, 2, 2, 2, 1, 2)) return 2;
+    if (sc_is_layered(hs, 3, 3, 3, 3, 2, 2)) return 3;
+    if (sc_is_layered(hs, 1, 1, 1, 3, 1, 2)) return 4;
+    if (sc_is_layered(hs, 2, 2, 2, 2, 2, 2)) return 5;
+    return 0;
+}
+
+int sc_run_f32(const ScRun& r) {
+    if (r.op == SC_OP_ROLLOUT && r.mode == SCG_MODE_FAST_F32) {
+        switch (r.variant) {
+            case 1: return sc_launch_layered<float, 1, 1, 1, 1, 1, 2, 128, 4>(r);
+            case 2: return sc_launch_layered<float, 2, 2, 2, 2, 1, 2, 128, 4>(r);
+            case 3: return sc_launch_layered<float, 3, 3, 3, 3, 2, 2, 128, 3>(r);
+            case 4: return sc_launch_layered<float, 1, 1, 1, 3, 1, 2, 128, 4>(r);
+            case 5: return sc_launch_layered<float, 2, 2, 2, 2, 2, 2, 128, 3>(r);
+            default: break;
+        }
+    }
+    return sc_launch_generic<float>(r);
+}
+
+size_t sc_devspec_size_f32() { return sizeof(ScDevSpec<float>); }
+int sc_build_devspec_f32(const ScHostSpec& hs, void** blob_out, void* devspec_out) {
+    return sc_build_devspec_t<float>(hs, blob_out, devspec_out);
+}
+
+}  // namespace scg

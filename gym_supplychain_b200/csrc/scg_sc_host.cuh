@@ -1,0 +1,174 @@
+// scg_sc_host.cuh -- host-side launch logic for the supply-chain kernels, templated on Real.
+// Included by scg_sc_f32.cu (default FMA contraction) and scg_sc_f64.cu (-fmad=false).
+#pragma once
+#include <cstring>
+
+#include "scg_internal.h"
+#include "scg_sc_static.cuh"
+
+namespace scg {
+
+// ---- device spec ---------------------------------------------------------------
+template <class Real>
+static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devspec_out) {
+    // pack every array into one host buffer (8-byte aligned sections), upload once
+    std::vector<unsigned char> buf;
+    auto put = [&buf](const void* src, size_t bytes) -> size_t {
+        size_t off = (buf.size() + 15) & ~(size_t)15;
+        buf.resize(off + (bytes ? bytes : 16));
+        if (bytes) memcpy(buf.data() + off, src, bytes);
+        return off;
+    };
+    auto put_real = [&](const std::vector<double>& v) -> size_t {
+        std::vector<Real> tmp(v.begin(), v.end());
+        return put(tmp.data(), tmp.size() * sizeof(Real));
+    };
+    auto put_int = [&](const std::vector<int>& v) -> size_t { return put(v.data(), v.size() * sizeof(int)); };
+    auto put_dbl = [&](const std::vector<double>& v) -> size_t { return put(v.data(), v.size() * sizeof(double)); };
+
+    size_t o_last = put_int(hs.last), o_ebeg = put_int(hs.ebeg), o_act = put_int(hs.act_off), o_lt = put_int(hs.lt_off);
+    size_t o_ret = put_int(hs.ret_idx), o_sup = put_int(hs.is_sup), o_pc = put_real(hs.proc_cap);
+    size_t o_s0 = put_real(hs.stock0), o_cap = put_real(hs.cap), o_hold = put_real(hs.hold), o_sc = put_real(hs.sup_cap);
+    size_t o_scost = put_real(hs.sup_cost), o_ratio = put_real(hs.ratio), o_pcost = put_real(hs.proc_cost);
+    size_t o_ms = put_real(hs.max_ship), o_edst = put_int(hs.edst), o_ecap = put_real(hs.ecap), o_ecost = put_real(hs.ecost);
+    size_t o_ibeg = put_int(hs.ibeg), o_itime = put_int(hs.itime), o_iamt = put_real(hs.iamt), o_dkind = put_int(hs.dkind);
+    size_t o_dlo = put_dbl(hs.dlo), o_dhi = put_dbl(hs.dhi), o_dstd = put_dbl(hs.dstd), o_dpk = put_dbl(hs.dpeaks);
+    size_t o_dmin = put_dbl(hs.dminavg), o_dmax = put_dbl(hs.dmaxavg);
+
+    unsigned char* d = nullptr;
+    SCG_CUDA(cudaMalloc(&d, buf.size()));
+    SCG_CUDA(cudaMemcpy(d, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    ScDevSpec<Real> sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.N = hs.N; sp.P = hs.P; sp.E = hs.E; sp.T = hs.T; sp.avgL = hs.avgL; sp.maxL = hs.maxL; sp.stochL = hs.stochL;
+    sp.RP = hs.RP; sp.A = hs.A; sp.O = hs.O; sp.K = hs.K; sp.ring = hs.ring; sp.heapcap = hs.heapcap;
+    sp.n_init = (int)hs.itime.size();
+    sp.c_unmet = (Real)hs.c_unmet; sp.c_xstock = (Real)hs.c_xstock; sp.c_xproc = (Real)hs.c_xproc; sp.c_xship = (Real)hs.c_xship;
+#define SCG_P(T_, off) reinterpret_cast<const T_*>(d + (off))
+    sp.last = SCG_P(int, o_last); sp.ebeg = SCG_P(int, o_ebeg); sp.act_off = SCG_P(int, o_act); sp.lt_off = SCG_P(int, o_lt);
+    sp.ret_idx = SCG_P(int, o_ret); sp.is_sup = SCG_P(int, o_sup); sp.proc_cap = SCG_P(Real, o_pc);
+    sp.stock0 = SCG_P(Real, o_s0); sp.cap = SCG_P(Real, o_cap); sp.hold = SCG_P(Real, o_hold); sp.sup_cap = SCG_P(Real, o_sc);
+    sp.sup_cost = SCG_P(Real, o_scost); sp.ratio = SCG_P(Real, o_ratio); sp.proc_cost = SCG_P(Real, o_pcost);
+    sp.max_ship = SCG_P(Real, o_ms); sp.edst = SCG_P(int, o_edst); sp.ecap = SCG_P(Real, o_ecap); sp.ecost = SCG_P(Real, o_ecost);
+    sp.ibeg = SCG_P(int, o_ibeg); sp.itime = SCG_P(int, o_itime); sp.iamt = SCG_P(Real, o_iamt); sp.dkind = SCG_P(int, o_dkind);
+    sp.dlo = SCG_P(double, o_dlo); sp.dhi = SCG_P(double, o_dhi); sp.dstd = SCG_P(double, o_dstd); sp.dpeaks = SCG_P(double, o_dpk);
+    sp.dminavg = SCG_P(double, o_dmin); sp.dmaxavg = SCG_P(double, o_dmax);
+#undef SCG_P
+    memcpy(devspec_out, &sp, sizeof(sp));
+    *blob_out = d;
+    return SCG_OK;
+}
+
+// ---- layered-variant matching ----------------------------------------------------
+static inline bool sc_is_layered(const ScHostSpec& hs, int S, int F, int W, int R, int P, int L) {
+    if (hs.N != S + F + W + R || hs.P != P || hs.stochL || hs.avgL != L || hs.maxL != L || hs.ring != L) return false;
+    const int cnt[4] = {S, F, W, R};
+    const int base[4] = {0, S, S + F, S + F + W};
+    for (int e = 0; e < 4; ++e)
+        for (int j = 0; j < cnt[e]; ++j) {
+            const int n = base[e] + j;
+            const int D = hs.ebeg[n + 1] - hs.ebeg[n];
+            if ((hs.last[n] != 0) != (e == 3)) return false;
+            if (e == 3) { if (D != 0) return false; }
+            else {
+                if (D != cnt[e + 1]) return false;
+                for (int i = 0; i < D; ++i) if (hs.edst[hs.ebeg[n] + i] != base[e + 1] + i) return false;
+            }
+            if ((hs.proc_cap[n] > 0) != (e == 1)) return false;
+            for (int p = 0; p < P; ++p) {
+                if ((hs.sup_cap[n * P + p] > 0) != (e == 0)) return false;
+                if (!(hs.cap[n * P + p] > 0)) return false;
+                if (e == 1 && !(hs.ratio[n * P + p] > 0)) return false;
+            }
+        }
+    return true;
+}
+
+template <class Real, int S, int F, int W, int R, int P, int L>
+static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R, P, L>& c) {
+    memset(&c, 0, sizeof(c));
+    constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
+    for (int i = 0; i < NP; ++i) {
+        c.cap[i] = (Real)hs.cap[i]; c.hold[i] = (Real)hs.hold[i]; c.stock0[i] = (Real)hs.stock0[i];
+        c.max_ship[i] = (Real)hs.max_ship[i];
+        c.obs_stock[i] = (Real)(2.0 / hs.cap[i]);
+        c.obs_mid[i] = (Real)(2.0 / hs.max_ship[i]);
+        c.obs_last[i] = (Real)(2.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
+        for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) c.init_slot[i * L + hs.itime[k] - 1] += (Real)hs.iamt[k];
+    }
+    for (int i = 0; i < S * P; ++i) { c.sup_cap[i] = (Real)hs.sup_cap[i]; c.sup_cost[i] = (Real)hs.sup_cost[i]; }
+    for (int j = 0; j < F; ++j) {
+        c.proc_cap[j] = (Real)hs.proc_cap[S + j];
+        for (int p = 0; p < P; ++p) {
+            c.ratio[j * P + p] = (Real)hs.ratio[(S + j) * P + p];
+            c.inv_ratio[j * P + p] = (Real)(1.0 / hs.ratio[(S + j) * P + p]);
+            c.proc_cost[j * P + p] = (Real)hs.proc_cost[(S + j) * P + p];
+        }
+    }
+    for (int e = 0; e < E; ++e) {
+        c.ecap[e] = (Real)hs.ecap[e];
+        for (int p = 0; p < P; ++p) c.ecost[e * P + p] = (Real)hs.ecost[e * P + p];
+    }
+    c.c_unmet = (Real)hs.c_unmet; c.c_xstock = (Real)hs.c_xstock; c.c_xproc = (Real)hs.c_xproc; c.c_xship = (Real)hs.c_xship;
+    c.all_uniform = 1;
+    for (int p = 0; p < P; ++p) {
+        c.dlo[p] = (Real)hs.dlo[p]; c.dspan[p] = (Real)(hs.dhi[p] - hs.dlo[p]);
+        c.obs_dem[p] = (Real)(2.0 / (hs.dhi[p] - hs.dlo[p]));
+        c.dlo_i[p] = (int)hs.dlo[p]; c.dcount[p] = (int)hs.dhi[p] - (int)hs.dlo[p] + 1;
+        if (hs.dkind[p] != 0) c.all_uniform = 0;
+    }
+    c.T = hs.T;
+}
+
+template <class Real, int S, int F, int W, int R, int P, int L, int THREADS, int MINB>
+static int sc_launch_layered(const ScRun& r) {
+    using C = LayeredConsts<Real, S, F, W, R, P, L>;
+    using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
+    static_assert(sizeof(C) <= 3800, "constants must fit the kernel parameter bank");
+    C c;
+    sc_fill_consts<Real, S, F, W, R, P, L>(*r.hs, c);
+    const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
+    const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
+    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
+    const size_t smem = (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Real);
+    const long long per_block = THREADS;
+    const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
+    if (r.actions == nullptr) {
+        auto k = sc_layered_rollout<Real, S, F, W, R, P, L, true, THREADS, MINB>;
+        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, nullptr, (Real*)r.obs, (Real*)r.reward, r.done);
+    } else {
+        auto k = sc_layered_rollout<Real, S, F, W, R, P, L, false, THREADS, MINB>;
+        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, (const Real*)r.actions, (Real*)r.obs, (Real*)r.reward, r.done);
+    }
+    SCG_CUDA(cudaGetLastError());
+    return SCG_OK;
+}
+
+template <class Real>
+static int sc_launch_generic(const ScRun& r) {
+    const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
+    const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
+    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((st.n + threads - 1) / threads);
+    const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
+    const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
+    if (r.mode == SCG_MODE_EXACT_F64) {
+        if constexpr (sizeof(Real) == 8) {
+            sc_generic_kernel<double, 1><<<blocks, threads, 0, r.stream>>>(
+                sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
+        } else {
+            set_error("EXACT mode needs the fp64 translation unit");
+            return SCG_EINVAL;
+        }
+    } else {
+        sc_generic_kernel<Real, 0><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
+                                                                       (const Real*)r.actions, (Real*)r.obs, (Real*)r.reward, r.done);
+    }
+    SCG_CUDA(cudaGetLastError());
+    return SCG_OK;
+}
+
+}  // namespace scg

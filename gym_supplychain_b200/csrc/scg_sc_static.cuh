@@ -1,0 +1,377 @@
+// scg_sc_static.cuh -- compile-time "layered chain" kernels (FAST modes).
+//
+// For S suppliers -> F factories -> W wholesalers -> R retailers, full bipartite between
+// consecutive echelons, P products, constant lead time L (the reference's 2perstage /
+// NPerStage / linear presets: supplychain_2perstage_env.py:27-53, supplychain_Nperstage_env.py:4-35),
+// every loop of sc_step_nodes unrolls and the whole env state (N*P stocks + N*P*L ring slots)
+// lives in registers for the whole T-step rollout.  Per-node constants come from the kernel
+// parameter bank (constant memory, immediate operands).
+//
+// HBM traffic per env-step is just the I/O: the action row in, obs row + reward + done out.
+// Rows are env-major in global memory ([n_envs, A] / [n_envs, O]); a warp owns 32 consecutive
+// envs, i.e. one contiguous 32*A (32*O) element chunk per period, which it moves with 16-byte
+// coalesced accesses through a per-warp shared-memory tile; each lane then reads (writes) its
+// own row from (to) the tile with vector accesses chosen so that they are bank-conflict free.
+#pragma once
+#include "scg_sc_device.cuh"
+
+namespace scg {
+
+template <class Real, int S, int F, int W, int R, int P, int L>
+struct LayeredConsts {
+    static constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
+    Real cap[NP], hold[NP], stock0[NP], max_ship[NP], init_slot[NP * L];
+    Real obs_stock[NP], obs_mid[NP], obs_last[NP];       // 2/cap, 2/max_ship, 2/(max_ship*(maxL-avgL+1))
+    Real sup_cap[S * P], sup_cost[S * P];
+    Real proc_cap[F], ratio[F * P], inv_ratio[F * P], proc_cost[F * P];
+    Real ecap[E], ecost[E * P];
+    Real c_unmet, c_xstock, c_xproc, c_xship;
+    Real dlo[P], dspan[P], obs_dem[P];                   // obs_dem = 2/span
+    int dlo_i[P], dcount[P];                             // uniform generator: lo, hi-lo+1
+    int all_uniform;
+    int T;
+};
+
+template <class Real, int S, int F, int W, int R, int P_, int L_>
+struct LayeredTopo {
+    using C = LayeredConsts<Real, S, F, W, R, P_, L_>;
+    static constexpr bool kStatic = true;
+    static constexpr int kN = S + F + W + R, kP = P_, kL = L_;
+    static constexpr int kMaxD = (F > W ? (F > R ? F : R) : (W > R ? W : R));
+    static constexpr int kA = S * (P_ + P_ * F) + F * P_ * W + W * P_ * R;
+    static constexpr int kO = R * P_ + kN * P_ * (1 + L_) + 1;
+    static constexpr int kRP = R * P_;
+    const C& c;
+    __device__ __forceinline__ explicit LayeredTopo(const C& cc) : c(cc) {}
+    static __device__ __forceinline__ constexpr int ech(int n) { return n < S ? 0 : (n < S + F ? 1 : (n < S + F + W ? 2 : 3)); }
+    static __device__ __forceinline__ constexpr int nbase(int e) { return e == 0 ? 0 : (e == 1 ? S : (e == 2 ? S + F : S + F + W)); }
+    static __device__ __forceinline__ constexpr int loc(int n) { return n - nbase(ech(n)); }
+    static __device__ __forceinline__ constexpr int cnt(int e) { return e == 0 ? S : (e == 1 ? F : (e == 2 ? W : R)); }
+    __device__ __forceinline__ constexpr int N() const { return kN; }
+    __device__ __forceinline__ constexpr int P() const { return kP; }
+    __device__ __forceinline__ constexpr int avgL() const { return kL; }
+    __device__ __forceinline__ constexpr int maxL() const { return kL; }
+    __device__ __forceinline__ constexpr int ring() const { return kL; }
+    __device__ __forceinline__ int T() const { return c.T; }
+    __device__ __forceinline__ constexpr bool last(int n) const { return ech(n) == 3; }
+    __device__ __forceinline__ constexpr bool supplier(int n) const { return ech(n) == 0; }
+    __device__ __forceinline__ constexpr int ndest(int n) const { return ech(n) == 3 ? 0 : cnt(ech(n) + 1); }
+    __device__ __forceinline__ constexpr int ebeg(int n) const {
+        return ech(n) == 0 ? loc(n) * F : (ech(n) == 1 ? S * F + loc(n) * W : S * F + F * W + loc(n) * R);
+    }
+    __device__ __forceinline__ constexpr int edst(int e) const {
+        return e < S * F ? S + e % F : (e < S * F + F * W ? S + F + (e - S * F) % W : S + F + W + (e - S * F - F * W) % R);
+    }
+    __device__ __forceinline__ Real ecap(int e) const { return c.ecap[e]; }
+    __device__ __forceinline__ Real ecost(int e, int p) const { return c.ecost[e * kP + p]; }
+    __device__ __forceinline__ Real proc_cap(int n) const { return ech(n) == 1 ? c.proc_cap[loc(n)] : (Real)0; }
+    __device__ __forceinline__ Real cap(int n, int p) const { return c.cap[n * kP + p]; }
+    __device__ __forceinline__ Real hold(int n, int p) const { return c.hold[n * kP + p]; }
+    __device__ __forceinline__ Real sup_cap(int n, int p) const { return c.sup_cap[loc(n) * kP + p]; }
+    __device__ __forceinline__ Real sup_cost(int n, int p) const { return c.sup_cost[loc(n) * kP + p]; }
+    __device__ __forceinline__ Real ratio(int n, int p) const { return ech(n) == 1 ? c.ratio[loc(n) * kP + p] : (Real)1; }
+    __device__ __forceinline__ Real proc_cost(int n, int p) const { return ech(n) == 1 ? c.proc_cost[loc(n) * kP + p] : (Real)0; }
+    __device__ __forceinline__ Real max_ship(int n, int p) const { return c.max_ship[n * kP + p]; }
+    __device__ __forceinline__ constexpr int act_off(int n) const {
+        return ech(n) == 0 ? loc(n) * (kP + kP * F)
+                           : (ech(n) == 1 ? S * (kP + kP * F) + loc(n) * kP * W
+                                          : (ech(n) == 2 ? S * (kP + kP * F) + F * kP * W + loc(n) * kP * R : kA));
+    }
+    __device__ __forceinline__ constexpr int lt_off(int) const { return 0; }
+    __device__ __forceinline__ constexpr int ret_idx(int n) const { return loc(n); }
+    __device__ __forceinline__ Real c_unmet() const { return c.c_unmet; }
+    __device__ __forceinline__ Real c_xstock() const { return c.c_xstock; }
+    __device__ __forceinline__ Real c_xproc() const { return c.c_xproc; }
+    __device__ __forceinline__ Real c_xship() const { return c.c_xship; }
+
+    __device__ __forceinline__ constexpr bool has_supply(int, int) const { return true; }
+    __device__ __forceinline__ constexpr bool can_ship(int, int) const { return true; }
+    __device__ __forceinline__ Real div_ratio(Real x, int n, int p) const {
+        if constexpr (sizeof(Real) == 8) return x / c.ratio[loc(n) * kP + p];
+        else return x * c.inv_ratio[loc(n) * kP + p];
+    }
+    // D folds to a constant after unrolling, so exactly one branch survives
+    __device__ __forceinline__ void ship_cuts(const Real* v, int D, Real limit, Real* out) const;
+};
+
+// sorted-cuts for a compile-time D (registers only)
+template <class Real, int D>
+__device__ __forceinline__ void ship_cuts_static(const Real* v, Real limit, Real* out) {
+    Real sv[D]; int si[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { sv[i] = v[i]; si[i] = i; }
+#pragma unroll
+    for (int a = 0; a < D - 1; ++a)
+#pragma unroll
+        for (int b = 0; b < D - 1 - a; ++b) {
+            // adjacent compare-exchange (bubble network): stable, strict '>' keeps index order on ties
+            const bool sw = sv[b] > sv[b + 1];
+            const Real x = sw ? sv[b + 1] : sv[b], y = sw ? sv[b] : sv[b + 1];
+            const int ix = sw ? si[b + 1] : si[b], iy = sw ? si[b] : si[b + 1];
+            sv[b] = x; sv[b + 1] = y; si[b] = ix; si[b + 1] = iy;
+        }
+    Real left = limit, prev = (Real)0, amt[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        Real a = (sv[k] - prev) * limit;
+        if (a > left) a = left;
+        amt[k] = a; left -= a; prev = sv[k];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        Real o = (Real)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o = (si[k] == i) ? amt[k] : o;
+        out[i] = o;
+    }
+}
+
+template <class Real, int S, int F, int W, int R, int P_, int L_>
+__device__ __forceinline__ void LayeredTopo<Real, S, F, W, R, P_, L_>::ship_cuts(const Real* v, int D, Real limit, Real* out) const {
+    if (D == F) ship_cuts_static<Real, F>(v, limit, out);
+    else if (D == W) ship_cuts_static<Real, W>(v, limit, out);
+    else ship_cuts_static<Real, R>(v, limit, out);
+}
+
+// ---------------------------------------------------------------------------------
+// register-resident state
+// ---------------------------------------------------------------------------------
+template <class Real, int NP, int L>
+struct RingRegs {
+    static constexpr bool kTwoPhase = true;
+    static constexpr bool kExactObs = false;
+    Real stock[NP];
+    Real slot[NP * L];
+    __device__ __forceinline__ Real get_stock(int np) const { return stock[np]; }
+    __device__ __forceinline__ void set_stock(int np, Real v) { stock[np] = v; }
+    __device__ __forceinline__ Real slot_at(int np, int k) const { return slot[np * L + k]; }
+    __device__ __forceinline__ Real arrive(int np, int) {
+        const Real a = slot[np * L];
+#pragma unroll
+        for (int k = 0; k + 1 < L; ++k) slot[np * L + k] = slot[np * L + k + 1];
+        slot[np * L + L - 1] = (Real)0;
+        return a;
+    }
+    __device__ __forceinline__ void push(int np, int, int /*lt == L*/, Real amount) { slot[np * L + L - 1] += amount; }
+};
+
+// Reads one env's row of LEN elements out of the warp tile, 16/8/4 bytes at a time.  All
+// indices are compile-time constants after unrolling, so the chunk cache folds away.
+template <class Real, int LEN>
+struct RowReader {
+    static constexpr int BYTES = LEN * (int)sizeof(Real);
+    static constexpr int VB = (BYTES % 16 == 0) ? 16 : ((BYTES % 8 == 0) ? 8 : (int)sizeof(Real));
+    static constexpr int VW = VB / (int)sizeof(Real);     // elements per vector access
+    const Real* row;
+    Real cur[VW];
+    int cur_chunk;
+    __device__ __forceinline__ explicit RowReader(const Real* r) : row(r), cur_chunk(-1) {}
+    __device__ __forceinline__ void load(int chunk) {
+        if constexpr (VB == 16 && sizeof(Real) == 4) {
+            const float4 q = reinterpret_cast<const float4*>(row)[chunk];
+            cur[0] = q.x; cur[1] = q.y; cur[2] = q.z; cur[3] = q.w;
+        } else if constexpr (VB == 16 && sizeof(Real) == 8) {
+            const double2 d = reinterpret_cast<const double2*>(row)[chunk];
+            cur[0] = d.x; cur[1] = d.y;
+        } else if constexpr (VB == 8 && sizeof(Real) == 4) {
+            const float2 q = reinterpret_cast<const float2*>(row)[chunk]; cur[0] = q.x; cur[1] = q.y;
+        } else {
+            cur[0] = row[chunk];
+        }
+        cur_chunk = chunk;
+    }
+    __device__ __forceinline__ Real get(int idx) {
+        const int chunk = idx / VW;
+        if (chunk != cur_chunk) load(chunk);
+        Real r = cur[0];
+#pragma unroll
+        for (int j = 1; j < VW; ++j) r = (idx % VW == j) ? cur[j] : r;
+        return r;
+    }
+};
+
+template <class Real, bool RANDOM, int A>
+struct StaticActions {
+    RowReader<Real, A> rd;
+    RngKey key; unsigned long long genv; unsigned episode; int t;
+    Philox4 blk; int blk_id;
+    __device__ __forceinline__ StaticActions(const Real* row, RngKey k, unsigned long long g, unsigned ep, int tt)
+        : rd(row), key(k), genv(g), episode(ep), t(tt), blk_id(-1) {}
+    __device__ __forceinline__ Real get(int idx) {
+        if constexpr (!RANDOM) return rd.get(idx);
+        else {
+            const int b = idx >> 2;
+            if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
+            return (Real)action_from_word(pick_word(blk, idx & 3));
+        }
+    }
+};
+
+template <int L> struct ConstLeadtime { __device__ __forceinline__ constexpr int get(int) const { return L; } };
+
+template <int RP> struct RegDemand {
+    int cur_[RP], next_[RP];
+    __device__ __forceinline__ int cur(int rp, int) const { return cur_[rp]; }
+    __device__ __forceinline__ int next(int rp, int) const { return next_[rp]; }
+};
+
+template <class Real> struct SmemObs {
+    Real* row;
+    __device__ __forceinline__ void put(int idx, Real v) { row[idx] = v; }
+};
+
+// contiguous warp copy, 16 B per lane when both sides are 16-byte aligned
+template <class Real>
+__device__ __forceinline__ void warp_copy(Real* __restrict__ dst, const Real* __restrict__ src, int count, int lane) {
+    const bool vec = ((((size_t)dst) | ((size_t)src)) & 15) == 0;
+    constexpr int VW = 16 / (int)sizeof(Real);
+    if (vec) {
+        const int nv = count / VW;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+        for (int i = lane; i < nv; i += 32) d4[i] = s4[i];
+        for (int i = nv * VW + lane; i < count; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// the fused rollout kernel
+// ---------------------------------------------------------------------------------
+template <class Real, int S, int F, int W, int R, int P, int L, bool RANDOM_ACT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L> c, ScDevSpec<Real> sp, ScState<Real> st,
+                   ScInputs in, int n_steps, const Real* __restrict__ actions, Real* __restrict__ obs,
+                   Real* __restrict__ reward, unsigned char* __restrict__ done) {
+    using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
+    constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Real* s_act = reinterpret_cast<Real*>(smem_raw) + (size_t)warp * 32 * (A + O);
+    Real* s_obs = s_act + 32 * A;
+    const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * 32;
+    const long long env = env0 + lane;
+    const long long n = st.n;
+    const bool active = env < n;
+    const int n_here = env0 >= n ? 0 : (int)((n - env0) < 32 ? (n - env0) : 32);
+    const Tp tp(c);
+    ReturnStats rs; rs.init();
+
+    RingRegs<Real, NP, L> pp;
+    RegDemand<RP> dm;
+    int t = 0; unsigned episode = 0; double ep_ret = 0.0;
+    const unsigned long long genv = (unsigned long long)(in.first_env + env);
+
+    auto fetch_next_demand = [&](int row) {
+        if (c.all_uniform && in.inj_demand == nullptr) {
+#pragma unroll
+            for (int b = 0; b < (RP + 3) / 4; ++b) {
+                const Philox4 blk = rng_block(in.key, genv, episode, (unsigned)row, STREAM_DEMAND, (unsigned)b);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rp = 4 * b + j;
+                    if (rp < RP) dm.next_[rp] = uniform_int(pick_word(blk, j), c.dlo_i[rp % P], (unsigned)c.dcount[rp % P]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int rp = 0; rp < RP; ++rp) dm.next_[rp] = sc_demand(sp, in, n, env, episode, row, rp, rp % P);
+        }
+    };
+
+    if (active) {
+        t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) pp.stock[i] = st.stock[(long long)i * n + env];
+#pragma unroll
+        for (int i = 0; i < NP * L; ++i) pp.slot[i] = st.slot[(long long)i * n + env];
+        fetch_next_demand(t);
+    }
+
+    for (int s = 0; s < n_steps; ++s) {
+        const long long io0 = (long long)s * n + env0;
+        __syncwarp();
+        if (!RANDOM_ACT && n_here > 0) warp_copy<Real>(s_act, actions + io0 * A, n_here * A, lane);
+        __syncwarp();
+        if (active) {
+            SmemObs<Real> ow{s_obs + lane * O};
+            Real r = (Real)0;
+            bool fin = true;
+            if (t < c.T) {
+                ++t;
+#pragma unroll
+                for (int rp = 0; rp < RP; ++rp) dm.cur_[rp] = dm.next_[rp];
+                StaticActions<Real, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
+                ConstLeadtime<L> lr;
+                const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+                r = -cost;
+                ep_ret += (double)r;
+                fin = (t == c.T);
+                if (fin) {
+                    rs.add(ep_ret);
+                    if (in.auto_reset) {
+                        ++episode; t = 0; ep_ret = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) pp.stock[i] = c.stock0[i];
+#pragma unroll
+                        for (int i = 0; i < NP * L; ++i) pp.slot[i] = c.init_slot[i];
+                    }
+                }
+                fetch_next_demand(t);
+            }
+            if (obs != nullptr) {
+                // observation (canonical per-arrival-time sums), :428-463 / :762-791
+                int o = 0;
+#pragma unroll
+                for (int rp = 0; rp < RP; ++rp) {
+                    const int p = rp % P;
+                    if constexpr (sizeof(Real) == 8)
+                        ow.put(o++, obs_norm<Real>(((Real)dm.next_[rp] - c.dlo[p]) / c.dspan[p]));
+                    else
+                        ow.put(o++, clamp_pm1<Real>(((Real)dm.next_[rp] - c.dlo[p]) * c.obs_dem[p] - (Real)1));
+                }
+#pragma unroll
+                for (int nn = 0; nn < N; ++nn) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const int np = nn * P + p;
+                        if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>(pp.stock[np] / c.cap[np]));
+                        else ow.put(o++, clamp_pm1<Real>(pp.stock[np] * c.obs_stock[np] - (Real)1));
+                    }
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const int np = nn * P + p;
+#pragma unroll
+                        for (int k = 0; k + 1 < L; ++k) {
+                            if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>(pp.slot[np * L + k] / c.max_ship[np]));
+                            else ow.put(o++, clamp_pm1<Real>(pp.slot[np * L + k] * c.obs_mid[np] - (Real)1));
+                        }
+                        if constexpr (sizeof(Real) == 8)
+                            ow.put(o++, obs_norm<Real>(pp.slot[np * L + L - 1] / (c.max_ship[np] * (Real)1)));
+                        else
+                            ow.put(o++, clamp_pm1<Real>(pp.slot[np * L + L - 1] * c.obs_last[np] - (Real)1));
+                    }
+                }
+                if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
+                else ow.put(o++, clamp_pm1<Real>((Real)(c.T - t) * ((Real)2 / (Real)c.T) - (Real)1));
+            }
+            reward[io0 + lane] = r;
+            done[io0 + lane] = fin ? 1 : 0;
+        }
+        __syncwarp();
+        if (obs != nullptr && n_here > 0) warp_copy<Real>(obs + io0 * O, s_obs, n_here * O, lane);
+    }
+
+    if (active) {
+        st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) st.stock[(long long)i * n + env] = pp.stock[i];
+#pragma unroll
+        for (int i = 0; i < NP * L; ++i) st.slot[(long long)i * n + env] = pp.slot[i];
+    }
+    rs.flush(st.stats);
+}
+
+}  // namespace scg

@@ -1,0 +1,159 @@
+"""CPU-side checks of the product's host layer: presets vs the reference's captured nodes_info, spec
+sizes, registry ids, the C-ABI library (loads, exports every symbol of include/scg.h, validates specs
+and fails loudly without a GPU).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gym_supplychain_b200 as gsc
+from golden_util import load, sc_cases
+from gym_supplychain_b200 import _lib, presets
+from gym_supplychain_b200.spec import FlatSpec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PRESET_OF = {"SupplyChainNPerStage": presets.n_per_stage, "SupplyChain2perStageEnv": presets.two_per_stage,
+             "SupplyChain2perStageSeasonalEnv": presets.two_per_stage_seasonal,
+             "SupplyChainMultiProduct": presets.multi_product,
+             "SupplyChainMultiProduct_IncreasingCosts": presets.multi_product_increasing_costs,
+             "SupplyChainMultiProduct_DemConfigByProd": presets.multi_product_dem_by_prod}
+
+
+def _norm(x):
+    if isinstance(x, tuple):
+        return [_norm(v) for v in x]
+    if isinstance(x, list):
+        return [_norm(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _norm(v) for k, v in x.items()}
+    return x
+
+
+@pytest.mark.parametrize("name", sc_cases())
+def test_presets_reproduce_reference_nodes_info(name):
+    meta, _ = load("sc", name)
+    if meta["cls"] not in PRESET_OF:
+        pytest.skip("explicit nodes_info case")
+    info, kw = PRESET_OF[meta["cls"]](**meta["ctor_kwargs"])
+    assert list(info.keys()) == list(meta["nodes_info"].keys())          # node (= act) order
+    assert _norm(info) == meta["nodes_info"]
+    ref_kw = meta["env_kwargs"]
+    for k, v in ref_kw.items():
+        assert _norm(kw[k]) == v, k
+
+
+def test_main_demo_chain_matches_golden():
+    meta, _ = load("sc", "supplychain_v0_main")
+    info, kw = presets.main_demo_chain(total_time_steps=120)
+    assert _norm(info) == meta["nodes_info"] and list(info) == list(meta["nodes_info"])
+    for k, v in meta["ctor_kwargs"].items():
+        if k != "nodes_info":
+            assert _norm(kw[k]) == v, k
+
+
+@pytest.mark.parametrize("name", sc_cases())
+def test_flat_spec_sizes_match_reference(name):
+    meta, _ = load("sc", name)
+    f = FlatSpec(meta["nodes_info"], **meta["env_kwargs"])
+    assert (f.N, f.P, f.T) == (meta["N"], meta["P"], meta["T"])
+    assert f.n_actions == meta["A"] and f.n_obs == meta["O"] and f.n_leadtimes == meta["K"]
+    assert f.n_retailers == meta["R"]
+
+
+def test_flat_spec_rejects_what_the_reference_rejects():
+    info, kw = presets.two_per_stage()
+    bad = dict(info)
+    bad["Supplier1"] = dict(bad["Supplier1"], stock_capacity=1.5)              # float -> ValueError (:186-189)
+    with pytest.raises(ValueError):
+        FlatSpec(bad, **kw)
+    bad["Supplier1"] = dict(info["Supplier1"], supply_cost=[1, 2, 3])          # wrong list length -> assert (:182)
+    with pytest.raises(AssertionError):
+        FlatSpec(bad, **kw)
+    with pytest.raises(AssertionError):                                         # fixed demand (:592)
+        FlatSpec(info, **dict(kw, demand_range=(5, 5)))
+    missing_cap = {k: {kk: vv for kk, vv in v.items() if kk != "stock_capacity"} for k, v in info.items()}
+    with pytest.raises(ValueError):                                             # default float('inf') (:529)
+        FlatSpec(missing_cap, **kw)
+
+
+def test_registry_has_reference_and_readme_ids():
+    ids = set(gsc.registered_ids())
+    for i in ("beergame-v0", "beergame-v2", "supplychain-v0", "sc-2perstage-v0", "sc-2perstage-seasonal-v0",
+              "sc-2perstage-multiproduct-v0", "sc-Nperstage-multiproduct-v0", "sc-2perstage-multiproduct-inccosts-v0",
+              "sc-2perstage-multiproduct-v1", "sc-2perstage-multiproduct-inccosts-v1",
+              "supplychain-ntom-v0", "supplychain-oneonen-v0", "supplychain-linear-v0", "supplychain-2perstage-v0"):
+        assert i in ids
+    with pytest.raises(KeyError):
+        gsc.make("gym_supplychain:no-such-env-v0")
+
+
+def test_shapes_of_named_ids():
+    for preset, kw, A, O in ((presets.n_per_stage, dict(nodes_per_echelon=1, num_products=1), 4, 14),
+                             (presets.two_per_stage, {}, 14, 27),
+                             (presets.n_per_stage, dict(nodes_per_echelon=3), 60, 79),
+                             (presets.n_per_stage, dict(nodes_per_echelon=[1, 1, 1, 3], num_products=1), 6, 22),
+                             (presets.n_per_stage, dict(nodes_per_echelon=10), 620, None),
+                             (presets.n_per_stage, dict(nodes_per_echelon=[5, 4, 7, 10]), 246, None),
+                             (presets.n_per_stage, dict(nodes_per_echelon=[5, 4, 7, 10], num_products=4), 492, None)):
+        info, k = preset(**kw)
+        f = FlatSpec(info, **k)
+        assert f.n_actions == A
+        if O is not None:
+            assert f.n_obs == O
+
+
+# ---------------------------------------------------------------------------------------------
+# the C-ABI library
+# ---------------------------------------------------------------------------------------------
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "scg.h")).read()
+    return sorted(set(re.findall(r"SCG_API[^;(]*?\b(scg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(n for n, _, _ in _lib.PROTOTYPES) == syms      # the ctypes table covers the whole header
+    assert lib.scg_abi_version() == 1
+
+
+def test_create_validates_spec_then_fails_loudly_without_gpu():
+    import torch
+    lib = _lib.load()
+    info, kw = presets.two_per_stage()
+    f = FlatSpec(info, **kw)
+    opt = _lib.ScgOptions()
+    opt.n_envs, opt.device, opt.mode = 4, 0, _lib.MODE_FAST_F32
+    h = C.c_void_p()
+    s = f.c_struct()
+    s.n_products = 99                                            # spec errors are reported before any CUDA call
+    assert lib.scg_sc_create(C.byref(s), C.byref(opt), C.byref(h)) == -1
+    assert b"bad sizes" in lib.scg_last_error()
+    s = f.c_struct()
+    rc = lib.scg_sc_create(C.byref(s), C.byref(opt), C.byref(h))
+    if torch.cuda.is_available():
+        assert rc == 0
+        lib.scg_destroy(h)
+    else:
+        assert rc == -2 and b"no CPU fallback" in lib.scg_last_error()
+        with pytest.raises(gsc.ScgError):
+            gsc.make("supplychain-ntom-v0", num_envs=8)
+        with pytest.raises(gsc.ScgError):
+            gsc.make("beergame-v2")
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import or include it."""
+    pkg = os.path.join(ROOT, "gym_supplychain_b200")
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), fn
+                assert "oracle/" not in text and "sc_oracle" not in text and "gym_shim" not in text, fn
