@@ -108,7 +108,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -119,7 +119,7 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, skip=0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -130,7 +130,7 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[skip:]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
                 continue
@@ -181,7 +181,7 @@ def run_ours(args):
     n_total = n_local * world
     first, n_mine = shard_range(n_total, rank, world)
     assert n_mine == n_local
-    env = gsc.make(ENV_ID, num_envs=n_local, device=dev, seed=args.seed, first_env=first, auto_reset=True)
+    env = gsc.make(ENV_ID, num_envs=n_local, device=dev, seed=args.seed, first_env=first, auto_reset=True, mode=args.mode)
     assert env.n_actions == A and env.n_obs == O and env.scg_info.kernel_variant == 3
     env.reset()
 
@@ -200,13 +200,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # started before warm-up: NVML start-up must not perturb the timed region
     for _ in range(args.warmup):
         one_step()
     barrier()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    n_warm_samples = len(sampler.lines)
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,7 +224,7 @@ def run_ours(args):
     t_end.record()
     barrier()
     launches = env.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(skip=n_warm_samples) if rank == 0 else None
     elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
     kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
@@ -271,10 +271,11 @@ def run_ours(args):
         cnt, mean, std, mn, mx = summarize_stats(stats_total)
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32" if args.mode == "fast_f32" else "f32 I/O, f64 state+arithmetic",
+                "data": "synthetic",
                 "config": {"workload": ENV_ID + " (SupplyChainNPerStage(3): 12 nodes, 2 products, A=60, O=79), "
                                                 "fused %d-period rollout, fp32 random actions read from HBM" % T,
-                           "envs_per_gpu": n_local, "envs_total": n_total, "rollout_T": T, "mode": "fast_f32",
+                           "envs_per_gpu": n_local, "envs_total": n_total, "rollout_T": T, "mode": args.mode,
                            "bytes_per_env_step": BYTES_PER_ENV_STEP, "auto_reset": True,
                            "l2": "inputs+outputs per step are %.1f GB per GPU (> 126 MB L2): no flush needed"
                                  % (n_local * T * BYTES_PER_ENV_STEP / 1e9),
@@ -285,7 +286,7 @@ def run_ours(args):
                         "api": "scg_rollout_host (pinned host buffers)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "sc_layered_rollout<float,3,3,3,3,2,2>", "kernel_ms": kern_ms,
+                             "traffic": None, "kernel": "sc_layered_rollout<%s,float,3,3,3,3,2,2>" % ("float" if args.mode == "fast_f32" else "double"), "kernel_ms": kern_ms,
                              "peak_source": peak_src, "bytes_per_launch": n_local * T * BYTES_PER_ENV_STEP},
                 "cpu_baseline": cpu,
                 "episodes_finished": cnt, "mean_episode_return": mean}
@@ -304,9 +305,10 @@ def main():
     ap.add_argument("--rollout-T", type=int, default=128)
     ap.add_argument("--e2e-T", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-envs-per-worker", type=int, default=4)
+    ap.add_argument("--cpu-envs-per-worker", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--mode", default="fast_f32", choices=["fast_f32", "mixed"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -7,8 +7,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscg.so")
 
-MODE_FAST_F32, MODE_FAST_F64, MODE_EXACT_F64 = 0, 1, 2
-MODES = {"fast_f32": MODE_FAST_F32, "fast_f64": MODE_FAST_F64, "exact_f64": MODE_EXACT_F64}
+MODE_FAST_F32, MODE_FAST_F64, MODE_EXACT_F64, MODE_MIXED = 0, 1, 2, 3
+MODES = {"fast_f32": MODE_FAST_F32, "fast_f64": MODE_FAST_F64, "exact_f64": MODE_EXACT_F64, "mixed": MODE_MIXED}
 FLAG_FORCE_GENERIC = 1
 DEMAND_UNIFORM, DEMAND_NORMAL, DEMAND_SIN_NORMAL, DEMAND_SIN_UNIFORM = 0, 1, 2, 3
 

@@ -24,6 +24,7 @@ UNITS = {
     "scg_bg.cu": [],
     "scg_sc_f32.cu": [],
     "scg_sc_f64.cu": ["-fmad=false"],
+    "scg_sc_mixed.cu": [],
 }
 
 

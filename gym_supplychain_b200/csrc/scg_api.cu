@@ -171,7 +171,9 @@ static int sc_flatten(const ScgSupplyChainSpec* s, ScHostSpec& hs) {
             if (hs.itime[k] < 1) { set_error("initial arrival periods are 1-based"); return SCG_EINVAL; }
             if (hs.itime[k] > ring) ring = hs.itime[k];
         }
-        const int cap = (indeg[n] + (hs.is_sup[n] ? 1 : 0)) * (hs.maxL > hs.avgL ? hs.maxL : hs.avgL) + n_init_np;
+        // every source can have maxL entries in flight, plus the one it pushes in the current period BEFORE this
+        // node pops its arrivals (upstream nodes act first, supplychain_env.py:714)
+        const int cap = (indeg[n] + (hs.is_sup[n] ? 1 : 0)) * ((hs.maxL > hs.avgL ? hs.maxL : hs.avgL) + 1) + n_init_np;
         if (cap > heapcap) heapcap = cap;
     }
     if (ring > 64) { set_error("ring depth %d too large", ring); return SCG_EINVAL; }
@@ -239,6 +241,7 @@ static int sc_dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask
     r.op = op; r.n_steps = n_steps; r.reset_mask = mask; r.actions = actions; r.obs = obs; r.reward = reward; r.done = done;
     r.stream = stream;
     ++h->launches;
+    if (h->opt.mode == SCG_MODE_MIXED) return sc_run_mixed(r);
     return is_f64(h->opt.mode) ? sc_run_f64(r) : sc_run_f32(r);
 }
 
@@ -270,7 +273,7 @@ int scg_abi_version(void) { return SCG_ABI_VERSION; }
 static int check_options(const ScgOptions* opt) {
     if (!opt) { set_error("null options"); return SCG_EINVAL; }
     if (opt->n_envs < 1) { set_error("n_envs must be >= 1"); return SCG_EINVAL; }
-    if (opt->mode < 0 || opt->mode > 2) { set_error("bad mode %d", opt->mode); return SCG_EINVAL; }
+    if (opt->mode < 0 || opt->mode > 3) { set_error("bad mode %d", opt->mode); return SCG_EINVAL; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -297,11 +300,12 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     if (rc == SCG_OK) rc = sc_alloc_state(h);
     if (rc != SCG_OK) { scg_destroy(h); return rc; }
     h->variant = opt->mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(h->hs)
-               : opt->mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(h->hs) : 0;
+               : opt->mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(h->hs)
+               : opt->mode == SCG_MODE_MIXED ? sc_match_variant_mixed(h->hs) : 0;
     if (opt->flags & SCG_FLAG_FORCE_GENERIC) h->variant = 0;
     ScgInfo& I = h->info;
     I.n_envs = opt->n_envs; I.family = 0; I.mode = opt->mode; I.n_actions = h->hs.A; I.n_obs = h->hs.O;
-    I.n_demands = h->hs.RP; I.n_leadtimes = h->hs.K; I.total_time_steps = h->hs.T; I.elem_size = is_f64(opt->mode) ? 8 : 4;
+    I.n_demands = h->hs.RP; I.n_leadtimes = h->hs.K; I.total_time_steps = h->hs.T; I.elem_size = (is_f64(opt->mode) && opt->mode != SCG_MODE_MIXED) ? 8 : 4;
     I.ring_depth = h->hs.ring; I.heap_capacity = h->hs.heapcap; I.kernel_variant = h->variant; I.state_bytes = (int64_t)h->state_bytes;
     rc = dispatch(h, SC_OP_RESET, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc == SCG_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { set_error("initial reset failed: %s", cudaGetErrorString(e)); rc = SCG_ECUDA; } }

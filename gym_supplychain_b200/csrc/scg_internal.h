@@ -64,6 +64,8 @@ int sc_match_variant_f32(const ScHostSpec& hs);
 int sc_match_variant_f64(const ScHostSpec& hs);
 int sc_run_f32(const ScRun& r);
 int sc_run_f64(const ScRun& r);
+int sc_match_variant_mixed(const ScHostSpec& hs);
+int sc_run_mixed(const ScRun& r);
 size_t sc_devspec_size_f32();
 size_t sc_devspec_size_f64();
 // Build the device spec: uploads arrays into one device blob, fills the ScDevSpec<Real> struct (host memory).

@@ -498,12 +498,12 @@ __device__ __forceinline__ void sc_obs_heap(const Tp& tp, const ScDevSpec<double
 // ---------------------------------------------------------------------------------
 // readers/writers used by the generic kernels
 // ---------------------------------------------------------------------------------
-template <class Real>
+template <class Real, class Io>
 struct GlobalActions {                 // actions[(step*n + env)*A + idx]  or Philox when null
-    const Real* row; bool random; RngKey key; unsigned long long genv; unsigned episode; int t;
+    const Io* row; bool random; RngKey key; unsigned long long genv; unsigned episode; int t;
     Philox4 blk; int blk_id;
     __device__ __forceinline__ Real get(int idx) {
-        if (!random) return row[idx];
+        if (!random) return (Real)row[idx];
         const int b = idx >> 2;
         if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
         return (Real)action_from_word(pick_word(blk, idx & 3));
@@ -523,10 +523,10 @@ struct DynDemand {
     __device__ __forceinline__ int next(int rp, int p) const { return sc_demand(sp, in, n, env, episode, t, rp, p); }
 };
 
-template <class Real>
+template <class Real, class Io>
 struct GlobalObs {
-    Real* row;
-    __device__ __forceinline__ void put(int idx, Real v) { if (row) row[idx] = v; }
+    Io* row;
+    __device__ __forceinline__ void put(int idx, Real v) { if (row) row[idx] = (Io)v; }
 };
 
 // ---------------------------------------------------------------------------------
@@ -550,11 +550,11 @@ __device__ __forceinline__ void sc_write_obs(const DynTopoOps<Real>& tp, const S
     else sc_obs_ring<Real>(tp, sp, pp, t, dr, ow);
 }
 
-template <class Real, int MODE>
+template <class Real, class Io, int MODE>
 __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                                                          const unsigned char* __restrict__ reset_mask, int do_reset,
-                                                         const Real* __restrict__ actions, Real* __restrict__ obs,
-                                                         Real* __restrict__ reward, unsigned char* __restrict__ done) {
+                                                         const Io* __restrict__ actions, Io* __restrict__ obs,
+                                                         Io* __restrict__ reward, unsigned char* __restrict__ done) {
     const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = env < st.n;
     ReturnStats rs; rs.init();
@@ -570,20 +570,20 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
         }
         if (n_steps == 0) {       // reset(): emit the current observation
             DynDemand<Real> dr{sp, in, st.n, env, episode, t};
-            GlobalObs<Real> ow{obs ? obs + env * sp.O : nullptr};
+            GlobalObs<Real, Io> ow{obs ? obs + env * sp.O : nullptr};
             sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
         }
         for (int s = 0; s < n_steps; ++s) {
             const long long io = (long long)s * st.n + env;
-            GlobalObs<Real> ow{obs ? obs + io * sp.O : nullptr};
+            GlobalObs<Real, Io> ow{obs ? obs + io * sp.O : nullptr};
             if (t >= sp.T) {      // finished and not auto-reset: frozen
                 DynDemand<Real> dr{sp, in, st.n, env, episode, t};
                 sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
-                reward[io] = (Real)0; done[io] = 1;
+                reward[io] = (Io)0; done[io] = 1;
                 continue;
             }
             ++t;
-            GlobalActions<Real> ar{actions ? actions + io * sp.A : nullptr, actions == nullptr, in.key,
+            GlobalActions<Real, Io> ar{actions ? actions + io * sp.A : nullptr, actions == nullptr, in.key,
                                    (unsigned long long)(in.first_env + env), episode, t, Philox4{0, 0, 0, 0}, -1};
             DynLeadtimes<Real> lr{sp, in, st.n, env, episode, t};
             DynDemand<Real> dr{sp, in, st.n, env, episode, t};
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
                 }
             }
             sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
-            reward[io] = r; done[io] = fin ? 1 : 0;
+            reward[io] = (Io)r; done[io] = fin ? 1 : 0;
         }
         st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
     }

@@ -23,15 +23,15 @@ int sc_match_variant_f32(const ScHostSpec& hs) {
 int sc_run_f32(const ScRun& r) {
     if (r.op == SC_OP_ROLLOUT && r.mode == SCG_MODE_FAST_F32) {
         switch (r.variant) {
-            case 1: return sc_launch_layered<float, 1, 1, 1, 1, 1, 2, 128, 4>(r);
-            case 2: return sc_launch_layered<float, 2, 2, 2, 2, 1, 2, 128, 4>(r);
-            case 3: return sc_launch_layered<float, 3, 3, 3, 3, 2, 2, 128, 3>(r);
-            case 4: return sc_launch_layered<float, 1, 1, 1, 3, 1, 2, 128, 4>(r);
-            case 5: return sc_launch_layered<float, 2, 2, 2, 2, 2, 2, 128, 3>(r);
+            case 1: return sc_launch_layered<float, float, 1, 1, 1, 1, 1, 2, 128, 4>(r);
+            case 2: return sc_launch_layered<float, float, 2, 2, 2, 2, 1, 2, 128, 4>(r);
+            case 3: return sc_launch_layered<float, float, 3, 3, 3, 3, 2, 2, 128, 3>(r);
+            case 4: return sc_launch_layered<float, float, 1, 1, 1, 3, 1, 2, 128, 4>(r);
+            case 5: return sc_launch_layered<float, float, 2, 2, 2, 2, 2, 2, 128, 3>(r);
             default: break;
         }
     }
-    return sc_launch_generic<float>(r);
+    return sc_launch_generic<float, float>(r);
 }
 
 size_t sc_devspec_size_f32() { return sizeof(ScDevSpec<float>); }

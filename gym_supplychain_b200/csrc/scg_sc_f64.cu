@@ -15,13 +15,13 @@ int sc_match_variant_f64(const ScHostSpec& hs) {
 int sc_run_f64(const ScRun& r) {
     if (r.op == SC_OP_ROLLOUT && r.mode == SCG_MODE_FAST_F64) {
         switch (r.variant) {
-            case 1: return sc_launch_layered<double, 1, 1, 1, 1, 1, 2, 128, 3>(r);
-            case 2: return sc_launch_layered<double, 2, 2, 2, 2, 1, 2, 128, 3>(r);
-            case 4: return sc_launch_layered<double, 1, 1, 1, 3, 1, 2, 128, 3>(r);
+            case 1: return sc_launch_layered<double, double, 1, 1, 1, 1, 1, 2, 128, 3>(r);
+            case 2: return sc_launch_layered<double, double, 2, 2, 2, 2, 1, 2, 128, 3>(r);
+            case 4: return sc_launch_layered<double, double, 1, 1, 1, 3, 1, 2, 128, 3>(r);
             default: break;
         }
     }
-    return sc_launch_generic<double>(r);
+    return sc_launch_generic<double, double>(r);
 }
 
 size_t sc_devspec_size_f64() { return sizeof(ScDevSpec<double>); }

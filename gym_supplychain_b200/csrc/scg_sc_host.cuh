@@ -120,7 +120,7 @@ static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R,
     c.T = hs.T;
 }
 
-template <class Real, int S, int F, int W, int R, int P, int L, int THREADS, int MINB>
+template <class Real, class Io, int S, int F, int W, int R, int P, int L, int THREADS, int MINB>
 static int sc_launch_layered(const ScRun& r) {
     using C = LayeredConsts<Real, S, F, W, R, P, L>;
     using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
@@ -130,23 +130,23 @@ static int sc_launch_layered(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
-    const size_t smem = (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Real);
+    const size_t smem = (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
     if (r.actions == nullptr) {
-        auto k = sc_layered_rollout<Real, S, F, W, R, P, L, true, THREADS, MINB>;
+        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, true, THREADS, MINB>;
         SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, nullptr, (Real*)r.obs, (Real*)r.reward, r.done);
+        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, nullptr, (Io*)r.obs, (Io*)r.reward, r.done);
     } else {
-        auto k = sc_layered_rollout<Real, S, F, W, R, P, L, false, THREADS, MINB>;
+        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, false, THREADS, MINB>;
         SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, (const Real*)r.actions, (Real*)r.obs, (Real*)r.reward, r.done);
+        k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
     }
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;
 }
 
-template <class Real>
+template <class Real, class Io>
 static int sc_launch_generic(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
@@ -156,16 +156,18 @@ static int sc_launch_generic(const ScRun& r) {
     const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
     if (r.mode == SCG_MODE_EXACT_F64) {
-        if constexpr (sizeof(Real) == 8) {
-            sc_generic_kernel<double, 1><<<blocks, threads, 0, r.stream>>>(
+        // only the -fmad=false translation unit (Real = Io = double) may instantiate the exact kernel:
+        // a second copy compiled with FMA contraction would be an ODR clash and break bit-exactness
+        if constexpr (sizeof(Real) == 8 && sizeof(Io) == 8) {
+            sc_generic_kernel<double, double, 1><<<blocks, threads, 0, r.stream>>>(
                 sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
         } else {
             set_error("EXACT mode needs the fp64 translation unit");
             return SCG_EINVAL;
         }
     } else {
-        sc_generic_kernel<Real, 0><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
-                                                                       (const Real*)r.actions, (Real*)r.obs, (Real*)r.reward, r.done);
+        sc_generic_kernel<Real, Io, 0><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
+                                                                           (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
     }
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;

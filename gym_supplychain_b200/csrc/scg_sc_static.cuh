@@ -190,15 +190,15 @@ struct RowReader {
     }
 };
 
-template <class Real, bool RANDOM, int A>
+template <class Real, class Io, bool RANDOM, int A>
 struct StaticActions {
-    RowReader<Real, A> rd;
+    RowReader<Io, A> rd;
     RngKey key; unsigned long long genv; unsigned episode; int t;
     Philox4 blk; int blk_id;
-    __device__ __forceinline__ StaticActions(const Real* row, RngKey k, unsigned long long g, unsigned ep, int tt)
+    __device__ __forceinline__ StaticActions(const Io* row, RngKey k, unsigned long long g, unsigned ep, int tt)
         : rd(row), key(k), genv(g), episode(ep), t(tt), blk_id(-1) {}
     __device__ __forceinline__ Real get(int idx) {
-        if constexpr (!RANDOM) return rd.get(idx);
+        if constexpr (!RANDOM) return (Real)rd.get(idx);
         else {
             const int b = idx >> 2;
             if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
@@ -215,9 +215,9 @@ template <int RP> struct RegDemand {
     __device__ __forceinline__ int next(int rp, int) const { return next_[rp]; }
 };
 
-template <class Real> struct SmemObs {
-    Real* row;
-    __device__ __forceinline__ void put(int idx, Real v) { row[idx] = v; }
+template <class Real, class Io> struct SmemObs {
+    Io* row;
+    __device__ __forceinline__ void put(int idx, Real v) { row[idx] = (Io)v; }
 };
 
 // contiguous warp copy, 16 B per lane when both sides are 16-byte aligned
@@ -240,17 +240,17 @@ __device__ __forceinline__ void warp_copy(Real* __restrict__ dst, const Real* __
 // ---------------------------------------------------------------------------------
 // the fused rollout kernel
 // ---------------------------------------------------------------------------------
-template <class Real, int S, int F, int W, int R, int P, int L, bool RANDOM_ACT, int THREADS, int MINB>
+template <class Real, class Io, int S, int F, int W, int R, int P, int L, bool RANDOM_ACT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L> c, ScDevSpec<Real> sp, ScState<Real> st,
-                   ScInputs in, int n_steps, const Real* __restrict__ actions, Real* __restrict__ obs,
-                   Real* __restrict__ reward, unsigned char* __restrict__ done) {
+                   ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
+                   Io* __restrict__ reward, unsigned char* __restrict__ done) {
     using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
     constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Real* s_act = reinterpret_cast<Real*>(smem_raw) + (size_t)warp * 32 * (A + O);
-    Real* s_obs = s_act + 32 * A;
+    Io* s_act = reinterpret_cast<Io*>(smem_raw) + (size_t)warp * 32 * (A + O);
+    Io* s_obs = s_act + 32 * A;
     const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * 32;
     const long long env = env0 + lane;
     const long long n = st.n;
@@ -293,17 +293,17 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
         __syncwarp();
-        if (!RANDOM_ACT && n_here > 0) warp_copy<Real>(s_act, actions + io0 * A, n_here * A, lane);
+        if (!RANDOM_ACT && n_here > 0) warp_copy<Io>(s_act, actions + io0 * A, n_here * A, lane);
         __syncwarp();
         if (active) {
-            SmemObs<Real> ow{s_obs + lane * O};
+            SmemObs<Real, Io> ow{s_obs + lane * O};
             Real r = (Real)0;
             bool fin = true;
             if (t < c.T) {
                 ++t;
 #pragma unroll
                 for (int rp = 0; rp < RP; ++rp) dm.cur_[rp] = dm.next_[rp];
-                StaticActions<Real, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
+                StaticActions<Real, Io, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
                 ConstLeadtime<L> lr;
                 const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
                 r = -cost;
@@ -357,11 +357,11 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
                 if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
                 else ow.put(o++, clamp_pm1<Real>((Real)(c.T - t) * ((Real)2 / (Real)c.T) - (Real)1));
             }
-            reward[io0 + lane] = r;
+            reward[io0 + lane] = (Io)r;
             done[io0 + lane] = fin ? 1 : 0;
         }
         __syncwarp();
-        if (obs != nullptr && n_here > 0) warp_copy<Real>(obs + io0 * O, s_obs, n_here * O, lane);
+        if (obs != nullptr && n_here > 0) warp_copy<Io>(obs + io0 * O, s_obs, n_here * O, lane);
     }
 
     if (active) {

@@ -216,7 +216,7 @@ class SupplyChainEnv(_ScgEnvBase):
         if auto_reset is None:
             auto_reset = num_envs is not None
         torch = _torch()
-        self._io_dtype = torch.float32 if mode == "fast_f32" else torch.float64
+        self._io_dtype = torch.float32 if mode in ("fast_f32", "mixed") else torch.float64
         self._init_handle(_lib.load().scg_sc_create, self.flat.c_struct(), num_envs, device, mode, auto_reset, seed, first_env,
                           force_generic=force_generic)
         assert self.n_actions == self.flat.n_actions and self.n_obs == self.flat.n_obs

@@ -27,7 +27,7 @@
  *       actions [n_envs, A]   obs [n_envs, O]   reward [n_envs]   done [n_envs] (uint8)
  *     and for rollouts   actions [T, n_envs, A]  obs [T, n_envs, O]  reward/done [T, n_envs].
  *   - element type of actions/obs/reward follows the handle's mode:
- *       SCG_MODE_FAST_F32 -> float32;  SCG_MODE_FAST_F64 / SCG_MODE_EXACT_F64 -> float64;
+ *       SCG_MODE_FAST_F32 / SCG_MODE_MIXED -> float32;  SCG_MODE_FAST_F64 / SCG_MODE_EXACT_F64 -> float64;
  *       beer game -> int32 for all three.
  *   - one handle per GPU shard; a handle is not thread-safe, distinct handles are independent.
  */
@@ -60,6 +60,7 @@ extern "C" {
 #define SCG_MODE_FAST_F32   0  /* fp32 state in registers, pre-summed lead-time ring, canonical obs   */
 #define SCG_MODE_FAST_F64   1  /* same algorithm in fp64                                              */
 #define SCG_MODE_EXACT_F64  2  /* fp64 + CPython-heapq-exact in-transit queues: bit-exact vs reference */
+#define SCG_MODE_MIXED      3  /* fp32 actions/obs/reward in HBM, fp64 state and arithmetic on chip       */
 
 /* demand generator kinds (demands_generator.py:20-31) */
 #define SCG_DEMAND_UNIFORM         0  /* randint(lo, hi+1)                                   (:33-36) */
