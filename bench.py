@@ -191,9 +191,19 @@ def run_ours(args):
     rew = torch.empty((T, n_local), dtype=torch.float32, device=dev)
     done = torch.empty((T, n_local), dtype=torch.uint8, device=dev)
 
-    def one_step():
+    stats_total = torch.zeros(5, dtype=torch.float64, device=dev)
+
+    def one_step(ev_pair=None):
+        """One bench step: the fused rollout, then the episode-return statistics (all-reduced over ranks)."""
+        if ev_pair is not None:
+            ev_pair[0].record()
         env.rollout(T, acts, out=(obs, rew, done))
-        return allreduce_return_stats(env.return_stats(clear=True))
+        if ev_pair is not None:
+            ev_pair[1].record()
+        s = allreduce_return_stats(env.return_stats(clear=True))
+        stats_total[0:3] += s[0:3]
+        stats_total[3] = torch.minimum(stats_total[3], s[3])
+        stats_total[4] = torch.maximum(stats_total[4], s[4])
 
     def barrier():
         if world > 1:
@@ -203,24 +213,21 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # started before warm-up: NVML start-up must not perturb the timed region
-    for _ in range(args.warmup):
-        one_step()
+    warm_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for _ in range(args.warmup):             # identical code path to the timed loop (no lazy module loads left for it)
+        one_step(warm_ev)
     barrier()
     n_warm_samples = len(sampler.lines)
+    stats_total.zero_()
+    stats_total[3], stats_total[4] = 1e300, -1e300
+
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stats_total = torch.zeros(5, dtype=torch.float64, device=dev)
-    stats_total[3], stats_total[4] = 1e300, -1e300
     barrier()
     t_start.record()
     for k in range(args.steps):
-        ev[k][0].record()
-        env.rollout(T, acts, out=(obs, rew, done))
-        ev[k][1].record()
-        s = allreduce_return_stats(env.return_stats(clear=True))
-        stats_total[0:3] += s[0:3]
-        stats_total[3] = torch.minimum(stats_total[3], s[3]); stats_total[4] = torch.maximum(stats_total[4], s[4])
+        one_step(ev[k])
     t_end.record()
     barrier()
     launches = env.launch_count() - launches0

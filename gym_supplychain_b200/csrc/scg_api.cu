@@ -57,7 +57,9 @@ struct ScgEnv {
     // staging for *_host calls
     void* stage = nullptr;
     size_t stage_bytes = 0;
-    cudaStream_t hstream = nullptr;
+    cudaStream_t hstream = nullptr;                 // kernels of the *_host calls
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams (PCIe is full duplex)
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 static int check_handle(ScgHandle h) {
@@ -390,6 +392,13 @@ void scg_destroy(ScgHandle h) {
     if (!h) return;
     cudaSetDevice(h->opt.device);
     if (h->hstream) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
+    if (h->s_in) { cudaStreamSynchronize(h->s_in); cudaStreamDestroy(h->s_in); }
+    if (h->s_out) { cudaStreamSynchronize(h->s_out); cudaStreamDestroy(h->s_out); }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
     cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
     delete h;
 }
@@ -444,9 +453,18 @@ int scg_rollout(ScgHandle h, int32_t T, const void* actions, void* obs, void* re
 
 // ---- host-buffer variants ----------------------------------------------------------------
 static int ensure_stage(ScgEnv* h, size_t bytes) {
-    if (!h->hstream) SCG_CUDA(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    if (!h->hstream) {
+        SCG_CUDA(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+        SCG_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        SCG_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SCG_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            SCG_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+            SCG_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+    }
     if (h->stage_bytes >= bytes) return SCG_OK;
-    if (h->stage) { SCG_CUDA(cudaStreamSynchronize(h->hstream)); cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
+    if (h->stage) { SCG_CUDA(cudaDeviceSynchronize()); cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
     SCG_CUDA(cudaMalloc(&h->stage, bytes));
     h->stage_bytes = bytes;
     return SCG_OK;
@@ -476,29 +494,47 @@ int scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, voi
     if (rc != SCG_OK) return rc;
     const size_t n = (size_t)h->opt.n_envs, es = (size_t)h->info.elem_size;
     const size_t A = h->info.n_actions, O = h->info.n_obs;
-    // chunk the rollout so that the staging buffers stay under ~2 GiB
+    // The rollout is cut into chunks of `chunk` periods that flow through a 3-stage pipeline on three streams
+    // (H2D of chunk i+1 | kernel of chunk i | D2H of chunk i-1) with double-buffered staging, so that the two
+    // PCIe directions and the kernel overlap.  Env state lives in the handle, so chunking does not change results.
     const size_t per_step = n * ((actions ? A : 0) * es + (obs ? O : 0) * es + es + 1);
-    size_t chunk = per_step ? ((size_t)2 << 30) / per_step : (size_t)T;
+    size_t chunk = ((size_t)T + 7) / 8;
+    const size_t max_chunk = per_step ? ((size_t)1 << 30) / per_step : (size_t)T;
+    if (chunk > max_chunk) chunk = max_chunk;
     if (chunk < 1) chunk = 1;
-    if (chunk > (size_t)T) chunk = (size_t)T;
     const size_t b_act = align_up(actions ? chunk * n * A * es : 0, 256), b_obs = align_up(obs ? chunk * n * O * es : 0, 256);
     const size_t b_rew = align_up(chunk * n * es, 256), b_done = align_up(chunk * n, 256);
-    rc = ensure_stage(h, b_act + b_obs + b_rew + b_done);
+    const size_t b_set = b_act + b_obs + b_rew + b_done;
+    rc = ensure_stage(h, 2 * b_set);
     if (rc != SCG_OK) return rc;
-    unsigned char* d_act = (unsigned char*)h->stage;
-    unsigned char* d_obs = d_act + b_act;
-    unsigned char* d_rew = d_obs + b_obs;
-    unsigned char* d_done = d_rew + b_rew;
-    for (size_t s0 = 0; s0 < (size_t)T; s0 += chunk) {
+    size_t i = 0;
+    for (size_t s0 = 0; s0 < (size_t)T; s0 += chunk, ++i) {
+        const int b = (int)(i & 1);
         const size_t c = ((size_t)T - s0) < chunk ? ((size_t)T - s0) : chunk;
-        if (actions) SCG_CUDA(cudaMemcpyAsync(d_act, (const unsigned char*)actions + s0 * n * A * es, c * n * A * es, cudaMemcpyHostToDevice, h->hstream));
+        unsigned char* d_act = (unsigned char*)h->stage + (size_t)b * b_set;
+        unsigned char* d_obs = d_act + b_act;
+        unsigned char* d_rew = d_obs + b_obs;
+        unsigned char* d_done = d_rew + b_rew;
+        if (actions) {
+            if (i >= 2) SCG_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));        // kernel i-2 has consumed this buffer
+            SCG_CUDA(cudaMemcpyAsync(d_act, (const unsigned char*)actions + s0 * n * A * es, c * n * A * es,
+                                     cudaMemcpyHostToDevice, h->s_in));
+            SCG_CUDA(cudaEventRecord(h->ev_in[b], h->s_in));
+            SCG_CUDA(cudaStreamWaitEvent(h->hstream, h->ev_in[b], 0));
+        }
+        if (i >= 2) SCG_CUDA(cudaStreamWaitEvent(h->hstream, h->ev_out[b], 0));      // D2H i-2 has drained this buffer
         rc = dispatch(h, SC_OP_ROLLOUT, (int)c, nullptr, actions ? d_act : nullptr, obs ? d_obs : nullptr, d_rew, d_done, h->hstream);
         if (rc != SCG_OK) return rc;
-        if (obs) SCG_CUDA(cudaMemcpyAsync((unsigned char*)obs + s0 * n * O * es, d_obs, c * n * O * es, cudaMemcpyDeviceToHost, h->hstream));
-        SCG_CUDA(cudaMemcpyAsync((unsigned char*)reward + s0 * n * es, d_rew, c * n * es, cudaMemcpyDeviceToHost, h->hstream));
-        SCG_CUDA(cudaMemcpyAsync(done + s0 * n, d_done, c * n, cudaMemcpyDeviceToHost, h->hstream));
+        SCG_CUDA(cudaEventRecord(h->ev_k[b], h->hstream));
+        SCG_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_k[b], 0));
+        if (obs) SCG_CUDA(cudaMemcpyAsync((unsigned char*)obs + s0 * n * O * es, d_obs, c * n * O * es, cudaMemcpyDeviceToHost, h->s_out));
+        SCG_CUDA(cudaMemcpyAsync((unsigned char*)reward + s0 * n * es, d_rew, c * n * es, cudaMemcpyDeviceToHost, h->s_out));
+        SCG_CUDA(cudaMemcpyAsync(done + s0 * n, d_done, c * n, cudaMemcpyDeviceToHost, h->s_out));
+        SCG_CUDA(cudaEventRecord(h->ev_out[b], h->s_out));
     }
+    SCG_CUDA(cudaStreamSynchronize(h->s_out));
     SCG_CUDA(cudaStreamSynchronize(h->hstream));
+    SCG_CUDA(cudaStreamSynchronize(h->s_in));
     return SCG_OK;
 }
 

@@ -91,9 +91,9 @@ static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R,
     for (int i = 0; i < NP; ++i) {
         c.cap[i] = (Real)hs.cap[i]; c.hold[i] = (Real)hs.hold[i]; c.stock0[i] = (Real)hs.stock0[i];
         c.max_ship[i] = (Real)hs.max_ship[i];
-        c.obs_stock[i] = (Real)(2.0 / hs.cap[i]);
-        c.obs_mid[i] = (Real)(2.0 / hs.max_ship[i]);
-        c.obs_last[i] = (Real)(2.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
+        c.obs_stock[i] = (float)(1.0 / hs.cap[i]);
+        c.obs_mid[i] = (float)(1.0 / hs.max_ship[i]);
+        c.obs_last[i] = (float)(1.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
         for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) c.init_slot[i * L + hs.itime[k] - 1] += (Real)hs.iamt[k];
     }
     for (int i = 0; i < S * P; ++i) { c.sup_cap[i] = (Real)hs.sup_cap[i]; c.sup_cost[i] = (Real)hs.sup_cost[i]; }
@@ -113,24 +113,25 @@ static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R,
     c.all_uniform = 1;
     for (int p = 0; p < P; ++p) {
         c.dlo[p] = (Real)hs.dlo[p]; c.dspan[p] = (Real)(hs.dhi[p] - hs.dlo[p]);
-        c.obs_dem[p] = (Real)(2.0 / (hs.dhi[p] - hs.dlo[p]));
+        c.obs_dem[p] = (float)(1.0 / (hs.dhi[p] - hs.dlo[p]));
         c.dlo_i[p] = (int)hs.dlo[p]; c.dcount[p] = (int)hs.dhi[p] - (int)hs.dlo[p] + 1;
         if (hs.dkind[p] != 0) c.all_uniform = 0;
     }
     c.T = hs.T;
+    c.obs_time = (float)(1.0 / (double)hs.T);
 }
 
 template <class Real, class Io, int S, int F, int W, int R, int P, int L, int THREADS, int MINB>
 static int sc_launch_layered(const ScRun& r) {
     using C = LayeredConsts<Real, S, F, W, R, P, L>;
-    using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
+    using Tp = LayeredTopo<Real, sizeof(Io) == 8, S, F, W, R, P, L>;
     static_assert(sizeof(C) <= 3800, "constants must fit the kernel parameter bank");
     C c;
     sc_fill_consts<Real, S, F, W, R, P, L>(*r.hs, c);
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
-    const size_t smem = (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
+    const size_t smem = 128 + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
     if (r.actions == nullptr) {

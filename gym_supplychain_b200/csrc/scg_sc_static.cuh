@@ -21,18 +21,22 @@ template <class Real, int S, int F, int W, int R, int P, int L>
 struct LayeredConsts {
     static constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
     Real cap[NP], hold[NP], stock0[NP], max_ship[NP], init_slot[NP * L];
-    Real obs_stock[NP], obs_mid[NP], obs_last[NP];       // 2/cap, 2/max_ship, 2/(max_ship*(maxL-avgL+1))
+    float obs_stock[NP], obs_mid[NP], obs_last[NP];      // 1/cap, 1/max_ship, 1/(max_ship*(maxL-avgL+1)) (non-exact obs path)
     Real sup_cap[S * P], sup_cost[S * P];
     Real proc_cap[F], ratio[F * P], inv_ratio[F * P], proc_cost[F * P];
     Real ecap[E], ecost[E * P];
     Real c_unmet, c_xstock, c_xproc, c_xship;
-    Real dlo[P], dspan[P], obs_dem[P];                   // obs_dem = 2/span
+    Real dlo[P], dspan[P];
+    float obs_dem[P];                                    // 1/span
+    float obs_time;                                      // 1/T
     int dlo_i[P], dcount[P];                             // uniform generator: lo, hi-lo+1
     int all_uniform;
     int T;
 };
 
-template <class Real, int S, int F, int W, int R, int P_, int L_>
+// EXACT = true keeps IEEE divisions (fp64 I/O modes: obs/rewards comparable bit-for-bit with the generic
+// fp64 kernel); false multiplies by host-computed reciprocals (fp32 and mixed modes).
+template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_>
 struct LayeredTopo {
     using C = LayeredConsts<Real, S, F, W, R, P_, L_>;
     static constexpr bool kStatic = true;
@@ -87,47 +91,78 @@ struct LayeredTopo {
     __device__ __forceinline__ constexpr bool has_supply(int, int) const { return true; }
     __device__ __forceinline__ constexpr bool can_ship(int, int) const { return true; }
     __device__ __forceinline__ Real div_ratio(Real x, int n, int p) const {
-        if constexpr (sizeof(Real) == 8) return x / c.ratio[loc(n) * kP + p];
+        if constexpr (EXACT) return x / c.ratio[loc(n) * kP + p];
         else return x * c.inv_ratio[loc(n) * kP + p];
     }
     // D folds to a constant after unrolling, so exactly one branch survives
     __device__ __forceinline__ void ship_cuts(const Real* v, int D, Real limit, Real* out) const;
 };
 
-// sorted-cuts for a compile-time D (registers only)
+// SHIP cuts for a compile-time D, registers only.
+//
+// Reference semantics (supplychain_env.py:72-94): walk the destinations in ascending (value, index) order;
+// destination i gets (v_i - prev)*limit where prev is the value of its predecessor in that order (0 for the
+// first), never more than what is left of `limit`.  In exact arithmetic the "never more than what is left"
+// clamp is the same as capping every cut point at 1, so with
+//     before(j, i) := v_j < v_i or (v_j == v_i and j < i),   prev_i := max{ min(v_j, 1) : before(j, i) } or 0
+// the amount is (min(v_i, 1) - prev_i) * limit -- no sort, no scatter.  (The fp64-exact mode does not use
+// this: it runs the reference's sequential loop, scg_sc_device.cuh ship_cuts_dyn.)
 template <class Real, int D>
 __device__ __forceinline__ void ship_cuts_static(const Real* v, Real limit, Real* out) {
-    Real sv[D]; int si[D];
+    if constexpr (D == 1) {
+        const Real w0 = v[0] < (Real)1 ? v[0] : (Real)1;
+        out[0] = w0 * limit;
+    } else if constexpr (D <= 4) {
+        Real w[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) { sv[i] = v[i]; si[i] = i; }
+        for (int i = 0; i < D; ++i) w[i] = v[i] < (Real)1 ? v[i] : (Real)1;
 #pragma unroll
-    for (int a = 0; a < D - 1; ++a)
+        for (int i = 0; i < D; ++i) {
+            Real prev = (Real)0;
+            bool has = false;
 #pragma unroll
-        for (int b = 0; b < D - 1 - a; ++b) {
-            // adjacent compare-exchange (bubble network): stable, strict '>' keeps index order on ties
-            const bool sw = sv[b] > sv[b + 1];
-            const Real x = sw ? sv[b + 1] : sv[b], y = sw ? sv[b] : sv[b + 1];
-            const int ix = sw ? si[b + 1] : si[b], iy = sw ? si[b] : si[b + 1];
-            sv[b] = x; sv[b + 1] = y; si[b] = ix; si[b + 1] = iy;
+            for (int j = 0; j < D; ++j) {
+                if (j == i) continue;
+                const bool before = (j < i) ? (v[j] <= v[i]) : (v[j] < v[i]);
+                const Real cand = (has && prev > w[j]) ? prev : w[j];      // max over predecessors seen so far
+                prev = before ? cand : prev;
+                has = has || before;
+            }
+            out[i] = (w[i] - prev) * limit;
         }
-    Real left = limit, prev = (Real)0, amt[D];
+    } else {
+        Real sv[D]; int si[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        Real a = (sv[k] - prev) * limit;
-        if (a > left) a = left;
-        amt[k] = a; left -= a; prev = sv[k];
-    }
+        for (int i = 0; i < D; ++i) { sv[i] = v[i]; si[i] = i; }
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        Real o = (Real)0;
+        for (int a = 0; a < D - 1; ++a)
 #pragma unroll
-        for (int k = 0; k < D; ++k) o = (si[k] == i) ? amt[k] : o;
-        out[i] = o;
+            for (int b = 0; b < D - 1 - a; ++b) {
+                // adjacent compare-exchange (bubble network): stable, strict '>' keeps index order on ties
+                const bool sw = sv[b] > sv[b + 1];
+                const Real x = sw ? sv[b + 1] : sv[b], y = sw ? sv[b] : sv[b + 1];
+                const int ix = sw ? si[b + 1] : si[b], iy = sw ? si[b] : si[b + 1];
+                sv[b] = x; sv[b + 1] = y; si[b] = ix; si[b + 1] = iy;
+            }
+        Real left = limit, prev = (Real)0, amt[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            Real a = (sv[k] - prev) * limit;
+            if (a > left) a = left;
+            amt[k] = a; left -= a; prev = sv[k];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            Real o = (Real)0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) o = (si[k] == i) ? amt[k] : o;
+            out[i] = o;
+        }
     }
 }
 
-template <class Real, int S, int F, int W, int R, int P_, int L_>
-__device__ __forceinline__ void LayeredTopo<Real, S, F, W, R, P_, L_>::ship_cuts(const Real* v, int D, Real limit, Real* out) const {
+template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_>
+__device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_>::ship_cuts(const Real* v, int D, Real limit, Real* out) const {
     if (D == F) ship_cuts_static<Real, F>(v, limit, out);
     else if (D == W) ship_cuts_static<Real, W>(v, limit, out);
     else ship_cuts_static<Real, R>(v, limit, out);
@@ -217,8 +252,43 @@ template <int RP> struct RegDemand {
 
 template <class Real, class Io> struct SmemObs {
     Io* row;
-    __device__ __forceinline__ void put(int idx, Real v) { row[idx] = (Io)v; }
+    template <class V> __device__ __forceinline__ void put(int idx, V v) { row[idx] = (Io)v; }
 };
+
+// ---------------------------------------------------------------------------------
+// Blackwell/Hopper bulk async copies (TMA, 1-D): one elected lane moves a whole warp tile.
+//   global -> shared : cp.async.bulk + mbarrier complete_tx   (SASS UBLKCP)
+//   shared -> global : cp.async.bulk ... bulk_group
+//   L2 prefetch      : cp.async.bulk.prefetch.L2
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
 
 // contiguous warp copy, 16 B per lane when both sides are 16-byte aligned
 template <class Real>
@@ -245,11 +315,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
 sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L> c, ScDevSpec<Real> sp, ScState<Real> st,
                    ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
                    Io* __restrict__ reward, unsigned char* __restrict__ done) {
-    using Tp = LayeredTopo<Real, S, F, W, R, P, L>;
+    constexpr bool kExact = sizeof(Io) == 8;
+    using Tp = LayeredTopo<Real, kExact, S, F, W, R, P, L>;
     constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Io* s_act = reinterpret_cast<Io*>(smem_raw) + (size_t)warp * 32 * (A + O);
+    // smem: [one mbarrier per warp, padded to 128 B][per warp: action tile | obs tile]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
+    Io* s_act = reinterpret_cast<Io*>(smem_raw + 128) + (size_t)warp * 32 * (A + O);
     Io* s_obs = s_act + 32 * A;
     const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * 32;
     const long long env = env0 + lane;
@@ -258,6 +331,15 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
     const int n_here = env0 >= n ? 0 : (int)((n - env0) < 32 ? (n - env0) : 32);
     const Tp tp(c);
     ReturnStats rs; rs.init();
+
+    // bulk (TMA) copies need 16-byte aligned addresses and sizes; otherwise fall back to plain warp copies
+    const unsigned act_bytes = (unsigned)(n_here * A * (int)sizeof(Io)), obs_bytes = (unsigned)(n_here * O * (int)sizeof(Io));
+    const bool bulk_in = !RANDOM_ACT && n_here > 0 && (((size_t)actions) & 15) == 0 &&
+                         (((size_t)n * A * sizeof(Io)) & 15) == 0 && (act_bytes & 15) == 0 && ((32 * A * sizeof(Io)) & 15) == 0;
+    const bool bulk_out = obs != nullptr && n_here > 0 && (((size_t)obs) & 15) == 0 && (((size_t)n * O * sizeof(Io)) & 15) == 0 &&
+                          (obs_bytes & 15) == 0 && ((32 * (A + O) * sizeof(Io)) & 15) == 0;
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
 
     RingRegs<Real, NP, L> pp;
     RegDemand<RP> dm;
@@ -281,6 +363,11 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
         }
     };
 
+    // prologue: start moving the first action tile while the state is being loaded
+    if (bulk_in && n_steps > 0 && lane == 0) {
+        mbar_expect_tx(bar, act_bytes);
+        bulk_g2s(s_act, actions + env0 * A, act_bytes, bar);
+    }
     if (active) {
         t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env];
 #pragma unroll
@@ -290,79 +377,102 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
         fetch_next_demand(t);
     }
 
+#pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
-        __syncwarp();
-        if (!RANDOM_ACT && n_here > 0) warp_copy<Io>(s_act, actions + io0 * A, n_here * A, lane);
-        __syncwarp();
-        if (active) {
-            SmemObs<Real, Io> ow{s_obs + lane * O};
-            Real r = (Real)0;
-            bool fin = true;
-            if (t < c.T) {
-                ++t;
+        if (bulk_in) {
+            // tile s was requested one period ago (or in the prologue); ask L2 for tile s+1 now
+            if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
+            while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+        } else if (!RANDOM_ACT && n_here > 0) {
+            __syncwarp();
+            warp_copy<Io>(s_act, actions + io0 * A, n_here * A, lane);
+            __syncwarp();
+        }
+        Real r = (Real)0;
+        bool fin = true, stepped = false;
+        if (active && t < c.T) {
+            stepped = true;
+            ++t;
 #pragma unroll
-                for (int rp = 0; rp < RP; ++rp) dm.cur_[rp] = dm.next_[rp];
-                StaticActions<Real, Io, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
-                ConstLeadtime<L> lr;
-                const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
-                r = -cost;
-                ep_ret += (double)r;
-                fin = (t == c.T);
-                if (fin) {
-                    rs.add(ep_ret);
-                    if (in.auto_reset) {
-                        ++episode; t = 0; ep_ret = 0.0;
+            for (int rp = 0; rp < RP; ++rp) dm.cur_[rp] = dm.next_[rp];
+            StaticActions<Real, Io, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
+            ConstLeadtime<L> lr;
+            const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+            r = -cost;
+            ep_ret += (double)r;
+            fin = (t == c.T);
+            if (fin) {
+                rs.add(ep_ret);
+                if (in.auto_reset) {
+                    ++episode; t = 0; ep_ret = 0.0;
 #pragma unroll
-                        for (int i = 0; i < NP; ++i) pp.stock[i] = c.stock0[i];
+                    for (int i = 0; i < NP; ++i) pp.stock[i] = c.stock0[i];
 #pragma unroll
-                        for (int i = 0; i < NP * L; ++i) pp.slot[i] = c.init_slot[i];
-                    }
+                    for (int i = 0; i < NP * L; ++i) pp.slot[i] = c.init_slot[i];
                 }
-                fetch_next_demand(t);
             }
+        }
+        __syncwarp();                      // every lane is done with the action tile of period s
+        if (bulk_in && s + 1 < n_steps && lane == 0) {
+            // request tile s+1 now: it lands while the observation below is computed and stored
+            mbar_expect_tx(bar, act_bytes);
+            bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
+        }
+        if (bulk_out) {
+            if (lane == 0) bulk_wait_read_all();   // the previous obs tile has left shared memory
+            __syncwarp();
+        }
+        if (active) {
+            if (stepped) fetch_next_demand(t);   // demand row t: shown in this obs, consumed by the next period
             if (obs != nullptr) {
+                SmemObs<Real, Io> ow{s_obs + lane * O};
                 // observation (canonical per-arrival-time sums), :428-463 / :762-791
                 int o = 0;
+                auto unit = [](float x, float inv) { return fmaf(__saturatef(x * inv), 2.0f, -1.0f); };   // clip(2x-1, -1, 1)
 #pragma unroll
                 for (int rp = 0; rp < RP; ++rp) {
                     const int p = rp % P;
-                    if constexpr (sizeof(Real) == 8)
-                        ow.put(o++, obs_norm<Real>(((Real)dm.next_[rp] - c.dlo[p]) / c.dspan[p]));
-                    else
-                        ow.put(o++, clamp_pm1<Real>(((Real)dm.next_[rp] - c.dlo[p]) * c.obs_dem[p] - (Real)1));
+                    if constexpr (kExact) ow.put(o++, obs_norm<Real>(((Real)dm.next_[rp] - c.dlo[p]) / c.dspan[p]));
+                    else ow.put(o++, unit((float)(dm.next_[rp] - c.dlo_i[p]), c.obs_dem[p]));
                 }
 #pragma unroll
                 for (int nn = 0; nn < N; ++nn) {
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const int np = nn * P + p;
-                        if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>(pp.stock[np] / c.cap[np]));
-                        else ow.put(o++, clamp_pm1<Real>(pp.stock[np] * c.obs_stock[np] - (Real)1));
+                        if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.stock[np] / c.cap[np]));
+                        else ow.put(o++, unit((float)pp.stock[np], c.obs_stock[np]));
                     }
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const int np = nn * P + p;
 #pragma unroll
                         for (int k = 0; k + 1 < L; ++k) {
-                            if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>(pp.slot[np * L + k] / c.max_ship[np]));
-                            else ow.put(o++, clamp_pm1<Real>(pp.slot[np * L + k] * c.obs_mid[np] - (Real)1));
+                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * L + k] / c.max_ship[np]));
+                            else ow.put(o++, unit((float)pp.slot[np * L + k], c.obs_mid[np]));
                         }
-                        if constexpr (sizeof(Real) == 8)
-                            ow.put(o++, obs_norm<Real>(pp.slot[np * L + L - 1] / (c.max_ship[np] * (Real)1)));
-                        else
-                            ow.put(o++, clamp_pm1<Real>(pp.slot[np * L + L - 1] * c.obs_last[np] - (Real)1));
+                        if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * L + L - 1] / (c.max_ship[np] * (Real)1)));
+                        else ow.put(o++, unit((float)pp.slot[np * L + L - 1], c.obs_last[np]));
                     }
                 }
-                if constexpr (sizeof(Real) == 8) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
-                else ow.put(o++, clamp_pm1<Real>((Real)(c.T - t) * ((Real)2 / (Real)c.T) - (Real)1));
+                if constexpr (kExact) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
+                else ow.put(o++, unit((float)(c.T - t), c.obs_time));
             }
             reward[io0 + lane] = (Io)r;
             done[io0 + lane] = fin ? 1 : 0;
         }
-        __syncwarp();
-        if (obs != nullptr && n_here > 0) warp_copy<Io>(obs + io0 * O, s_obs, n_here * O, lane);
+        if (bulk_out) {
+            fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(obs + io0 * O, s_obs, obs_bytes); bulk_commit(); }
+        } else if (obs != nullptr && n_here > 0) {
+            __syncwarp();
+            warp_copy<Io>(obs + io0 * O, s_obs, n_here * O, lane);
+            __syncwarp();
+        }
     }
+    if (bulk_out && lane == 0) bulk_wait_all();    // shared memory must outlive the last bulk store
 
     if (active) {
         st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
