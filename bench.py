@@ -166,6 +166,7 @@ def run_ours(args):
     import gym_supplychain_b200 as gsc
     from gym_supplychain_b200.dist import allreduce_return_stats, shard_range, summarize_stats
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -181,9 +182,6 @@ def run_ours(args):
     n_total = n_local * world
     first, n_mine = shard_range(n_total, rank, world)
     assert n_mine == n_local
-    env = gsc.make(ENV_ID, num_envs=n_local, device=dev, seed=args.seed, first_env=first, auto_reset=True, mode=args.mode)
-    assert env.n_actions == A and env.n_obs == O and env.scg_info.kernel_variant == 3
-    env.reset()
 
     acts = torch.empty((T, n_local, A), dtype=torch.float32, device=dev)
     acts.uniform_(-1.0, 1.0)                                        # synthetic random policy, resident in HBM
@@ -191,54 +189,61 @@ def run_ours(args):
     rew = torch.empty((T, n_local), dtype=torch.float32, device=dev)
     done = torch.empty((T, n_local), dtype=torch.uint8, device=dev)
 
-    stats_total = torch.zeros(5, dtype=torch.float64, device=dev)
-
-    def one_step(ev_pair=None):
-        """One bench step: the fused rollout, then the episode-return statistics (all-reduced over ranks)."""
-        if ev_pair is not None:
-            ev_pair[0].record()
-        env.rollout(T, acts, out=(obs, rew, done))
-        if ev_pair is not None:
-            ev_pair[1].record()
-        s = allreduce_return_stats(env.return_stats(clear=True))
-        stats_total[0:3] += s[0:3]
-        stats_total[3] = torch.minimum(stats_total[3], s[3])
-        stats_total[4] = torch.maximum(stats_total[4], s[4])
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()                      # started before warm-up: NVML start-up must not perturb the timed region
-    warm_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    for _ in range(args.warmup):             # identical code path to the timed loop (no lazy module loads left for it)
-        one_step(warm_ev)
-    barrier()
-    n_warm_samples = len(sampler.lines)
-    stats_total.zero_()
-    stats_total[3], stats_total[4] = 1e300, -1e300
+    def measure(mode, steps, warmup, sample_clocks):
+        """Time `steps` bench steps of `mode`; returns (env, dict).  A step = fused rollout + stats all-reduce."""
+        env = gsc.make(ENV_ID, num_envs=n_local, device=dev, seed=args.seed, first_env=first, auto_reset=True, mode=mode)
+        assert env.n_actions == A and env.n_obs == O and env.scg_info.kernel_variant == 3
+        env.reset()
+        stats_total = torch.zeros(5, dtype=torch.float64, device=dev)
 
-    launches0 = env.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_start.record()
-    for k in range(args.steps):
-        one_step(ev[k])
-    t_end.record()
-    barrier()
-    launches = env.launch_count() - launches0
-    clocks = sampler.stop(skip=n_warm_samples) if rank == 0 else None
-    elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
-    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms, kern_ms = float(elapsed_ms), float(kern_ms)
-    value = n_total * T * args.steps / (elapsed_ms * 1e-3)
+        def one_step(ev_pair):
+            ev_pair[0].record()
+            env.rollout(T, acts, out=(obs, rew, done))
+            ev_pair[1].record()
+            s = allreduce_return_stats(env.return_stats(clear=True))
+            stats_total[0:3] += s[0:3]
+            stats_total[3] = torch.minimum(stats_total[3], s[3])
+            stats_total[4] = torch.maximum(stats_total[4], s[4])
+
+        sampler = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            sampler.start()                  # started before warm-up: NVML start-up must not perturb the timed region
+        warm_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for _ in range(warmup):              # identical code path to the timed loop (no lazy module loads left for it)
+            one_step(warm_ev)
+        barrier()
+        n_warm_samples = len(sampler.lines)
+        stats_total.zero_()
+        stats_total[3], stats_total[4] = 1e300, -1e300
+        launches0 = env.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_start.record()
+        for k in range(steps):
+            one_step(ev[k])
+        t_end.record()
+        barrier()
+        launches = env.launch_count() - launches0
+        clocks = sampler.stop(skip=n_warm_samples) if (rank == 0 and sample_clocks) else None
+        el = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+        km = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        el, km = float(el), float(km)
+        achieved = n_local * T * BYTES_PER_ENV_STEP / (km * 1e-3) / 1e9
+        return env, {"value": n_total * T * steps / (el * 1e-3), "elapsed_ms": el, "kernel_ms": km, "launches": launches,
+                     "clocks": clocks, "achieved_gbs": achieved, "stats": stats_total.clone()}
+
+    env, m = measure(args.mode, args.steps, args.warmup, True)
+    value, elapsed_ms, kern_ms, launches, clocks, stats_total = (m["value"], m["elapsed_ms"], m["kernel_ms"], m["launches"],
+                                                                  m["clocks"], m["stats"])
 
     # ---- e2e: host buffers through the C ABI (H2D actions, kernel, D2H obs/reward/done inside the timed region) ----
     Te = args.e2e_T
@@ -260,6 +265,20 @@ def run_ours(args):
     e2e_value = n_total * Te * args.e2e_steps / float(e2e_s)
     assert torch.isfinite(h_rew).all() and float(h_obs.abs().max()) <= 1.0
 
+    # ---- the other fp32-I/O mode, same buffers, shorter run (reported beside the headline, never as `value`) ----
+    alt = None
+    if not args.no_alt:
+        other = "fast_f32" if args.mode == "mixed" else "mixed"
+        del env
+        torch.cuda.empty_cache()
+        env, ma = measure(other, max(3, min(args.steps, 5)), 3, False)
+        peak_alt, _ = measured_peak()
+        alt = {other: {"value": ma["value"], "unit": "env-steps/s", "kernel_ms": ma["kernel_ms"],
+                       "roofline_frac": ma["achieved_gbs"] / peak_alt,
+                       "note": ("all-fp32 arithmetic: per-step reward error vs the reference up to 2e-6 relative (test tolerance "
+                                "5e-6), above the 1e-6 north-star bar, hence not the headline") if other == "fast_f32"
+                               else "fp32 I/O, fp64 state and arithmetic (1e-6 bar met)"}}
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -274,7 +293,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = n_local * T * BYTES_PER_ENV_STEP / (kern_ms * 1e-3) / 1e9
+        achieved = m["achieved_gbs"]
         cnt, mean, std, mn, mx = summarize_stats(stats_total)
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -295,7 +314,7 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "sc_layered_rollout<%s,float,3,3,3,3,2,2>" % ("float" if args.mode == "fast_f32" else "double"), "kernel_ms": kern_ms,
                              "peak_source": peak_src, "bytes_per_launch": n_local * T * BYTES_PER_ENV_STEP},
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "alt_modes": alt,
                 "episodes_finished": cnt, "mean_episode_return": mean}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -315,7 +334,8 @@ def main():
     ap.add_argument("--cpu-envs-per-worker", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--mode", default="fast_f32", choices=["fast_f32", "mixed"])
+    ap.add_argument("--mode", default="mixed", choices=["fast_f32", "mixed"])
+    ap.add_argument("--no-alt", action="store_true", help="skip the secondary measurement of the other fp32-I/O mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
