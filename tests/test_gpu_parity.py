@@ -408,3 +408,27 @@ def test_host_buffer_entry_points():
     env.rollout_host(T, acts, obs, rew, done)
     o, r, d = ref.rollout(T, acts.cuda())
     assert torch.equal(obs, o.cpu()) and torch.equal(rew, r.cpu()) and torch.equal(done, d.cpu())
+
+
+def test_integration_stub_host_calls_in_exact_mode():
+    """The ctypes calls INTEGRATION.md shows (scg_reset_host / scg_step_host, numpy buffers, exact_f64)."""
+    import ctypes as C
+    from gym_supplychain_b200 import _lib
+    from gym_supplychain_b200.spec import FlatSpec
+    meta, z = load("sc", "ntom")
+    lib = _lib.load()
+    spec = FlatSpec(meta["nodes_info"], **meta["env_kwargs"])
+    opt = _lib.ScgOptions(n_envs=1, first_env=0, seed=0, device=0, mode=_lib.MODE_EXACT_F64, auto_reset=0, flags=0)
+    h = C.c_void_p()
+    cs = spec.c_struct()
+    _lib.check(lib.scg_sc_create(C.byref(cs), C.byref(opt), C.byref(h)))
+    dem = torch.from_numpy(z["demand"][0].astype(np.int32)).reshape(361, 6, 1).contiguous().cuda()
+    _lib.check(lib.scg_inject(h, C.c_void_p(dem.data_ptr()), None))
+    obs, rew, done = np.empty(79), np.empty(1), np.empty(1, np.uint8)
+    _lib.check(lib.scg_reset_host(h, None, obs.ctypes.data))
+    assert np.array_equal(obs, z["obs"][0, 0])
+    for t in range(40):
+        a = np.ascontiguousarray(z["actions"][0, t])
+        _lib.check(lib.scg_step_host(h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+        assert np.array_equal(obs, z["obs"][0, t + 1]) and rew[0] == z["reward"][0, t] and not done[0]
+    lib.scg_destroy(h)
