@@ -360,15 +360,18 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (!tp.can_ship(n, p)) continue;                            // no SHIP action (:196-201)
                 Real over_ship = (Real)0, over_proc = (Real)0;
                 const Real s = pp.get_stock(np);
-                Real v[MAXD];
+                typename Ar::raw_t rv[MAXD];
                 // (read unconditionally so the staged-row reader sees straight-line code)
 #pragma unroll(Tp::kStatic ? MAXD : 1)
-                for (int i = 0; i < D; ++i) v[i] = denorm_action<Real>(ar.get(ai + i));
-                if (s > (Real)0) {
+                for (int i = 0; i < D; ++i) rv[i] = ar.get_raw(ai + i);
+                // The reference skips the whole block when stock <= 0 (:283).  The compile-time kernels run it with
+                // limit = 0 instead (every amount 0, nothing pushed, costs += 0): same result, no divergent branch.
+                if (Tp::kStatic || s > (Real)0) {
                     const Real c = tp.cap(n, p);
-                    const Real limit = c < s ? c : s;
+                    Real limit = c < s ? c : s;
+                    if (Tp::kStatic) limit = limit > (Real)0 ? limit : (Real)0;
                     Real out[MAXD], send[MAXD];
-                    tp.ship_cuts(v, D, limit, out);
+                    tp.ship_cuts(rv, D, limit, out);
                     const Real r = tp.ratio(n, p);
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) send[i] = out[i];
@@ -433,7 +436,10 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
 template <class Real>
 struct DynTopoOps : DynTopo<Real> {
     __device__ __forceinline__ explicit DynTopoOps(const ScDevSpec<Real>& s) : DynTopo<Real>(s) {}
-    __device__ __forceinline__ void ship_cuts(const Real* v, int D, Real limit, Real* out) const {
+    template <class RawT>
+    __device__ __forceinline__ void ship_cuts(const RawT* rv, int D, Real limit, Real* out) const {
+        Real v[SC_MAXD];
+        for (int i = 0; i < D; ++i) v[i] = denorm_action<Real>((Real)rv[i]);      // :697-698
         ship_cuts_dyn<Real, SC_MAXD>(v, D, limit, out);
     }
 };
@@ -502,12 +508,14 @@ template <class Real, class Io>
 struct GlobalActions {                 // actions[(step*n + env)*A + idx]  or Philox when null
     const Io* row; bool random; RngKey key; unsigned long long genv; unsigned episode; int t;
     Philox4 blk; int blk_id;
-    __device__ __forceinline__ Real get(int idx) {
-        if (!random) return (Real)row[idx];
+    using raw_t = Io;
+    __device__ __forceinline__ Io get_raw(int idx) {
+        if (!random) return row[idx];
         const int b = idx >> 2;
         if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
-        return (Real)action_from_word(pick_word(blk, idx & 3));
+        return (Io)action_from_word(pick_word(blk, idx & 3));
     }
+    __device__ __forceinline__ Real get(int idx) { return (Real)get_raw(idx); }
 };
 
 template <class Real>

@@ -95,7 +95,8 @@ struct LayeredTopo {
         else return x * c.inv_ratio[loc(n) * kP + p];
     }
     // D folds to a constant after unrolling, so exactly one branch survives
-    __device__ __forceinline__ void ship_cuts(const Real* v, int D, Real limit, Real* out) const;
+    template <class RawT>
+    __device__ __forceinline__ void ship_cuts(const RawT* rv, int D, Real limit, Real* out) const;
 };
 
 // SHIP cuts for a compile-time D, registers only.
@@ -104,68 +105,64 @@ struct LayeredTopo {
 // destination i gets (v_i - prev)*limit where prev is the value of its predecessor in that order (0 for the
 // first), never more than what is left of `limit`.  In exact arithmetic the "never more than what is left"
 // clamp is the same as capping every cut point at 1, so with
-//     before(j, i) := v_j < v_i or (v_j == v_i and j < i),   prev_i := max{ min(v_j, 1) : before(j, i) } or 0
-// the amount is (min(v_i, 1) - prev_i) * limit -- no sort, no scatter.  (The fp64-exact mode does not use
-// this: it runs the reference's sequential loop, scg_sc_device.cuh ship_cuts_dyn.)
-template <class Real, int D>
-__device__ __forceinline__ void ship_cuts_static(const Real* v, Real limit, Real* out) {
-    if constexpr (D == 1) {
-        const Real w0 = v[0] < (Real)1 ? v[0] : (Real)1;
-        out[0] = w0 * limit;
-    } else if constexpr (D <= 4) {
-        Real w[D];
+//     before(j, i) := v_j < v_i or (v_j == v_i and j < i),   prev_i := min(v_j, 1) of i's predecessor, or 0
+// the amount is (min(v_i, 1) - prev_i) * limit -- no sort, no scatter.  v = (a+1)/2 is monotone in the raw
+// action a, so the order predicates and the cap are evaluated on the RAW actions (fp32 compares even when
+// the arithmetic type is fp64) and only the final subtraction and product run in Real.
+// (The fp64-exact mode does not use this: it runs the reference's sequential loop, ship_cuts_dyn.)
+template <class Real, class RawT, int D>
+__device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real* out) {
+    Real w[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) w[i] = v[i] < (Real)1 ? v[i] : (Real)1;
+    for (int i = 0; i < D; ++i) {
+        const RawT capped = r[i] < (RawT)1 ? r[i] : (RawT)1;
+        w[i] = denorm_action<Real>((Real)capped);
+    }
+    if constexpr (D == 1) {
+        out[0] = w[0] * limit;
+    } else if constexpr (D == 2) {
+        const bool c01 = r[0] <= r[1];                       // 0 before 1
+        out[0] = (w[0] - (c01 ? (Real)0 : w[1])) * limit;
+        out[1] = (w[1] - (c01 ? w[0] : (Real)0)) * limit;
+    } else if constexpr (D == 3) {
+        const bool c01 = r[0] <= r[1], c02 = r[0] <= r[2], c12 = r[1] <= r[2];
+        // for destination i with the other two j < k:  bj = before(j,i), bk = before(k,i), bjk = before(j,k);
+        // predecessor = k if bk and (not bj or bjk), else j (if bj), else none
+        auto prev_of = [&](bool bj, bool bk, bool bjk, Real wj, Real wk) {
+            const Real cand = (bk && (!bj || bjk)) ? wk : wj;
+            return (bj || bk) ? cand : (Real)0;
+        };
+        out[0] = (w[0] - prev_of(!c01, !c02, c12, w[1], w[2])) * limit;
+        out[1] = (w[1] - prev_of(c01, !c12, c02, w[0], w[2])) * limit;
+        out[2] = (w[2] - prev_of(c02, c12, c01, w[0], w[1])) * limit;
+    } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             Real prev = (Real)0;
+            RawT rprev = (RawT)0;
             bool has = false;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 if (j == i) continue;
-                const bool before = (j < i) ? (v[j] <= v[i]) : (v[j] < v[i]);
-                const Real cand = (has && prev > w[j]) ? prev : w[j];      // max over predecessors seen so far
-                prev = before ? cand : prev;
+                const bool before = (j < i) ? (r[j] <= r[i]) : (r[j] < r[i]);
+                // among the predecessors keep the last one in (value, index) order
+                const bool later = !has || (j > 0 && (rprev <= r[j]));     // j ascending: ties go to the larger index
+                const bool take = before && later;
+                prev = take ? w[j] : prev;
+                rprev = take ? r[j] : rprev;
                 has = has || before;
             }
             out[i] = (w[i] - prev) * limit;
-        }
-    } else {
-        Real sv[D]; int si[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) { sv[i] = v[i]; si[i] = i; }
-#pragma unroll
-        for (int a = 0; a < D - 1; ++a)
-#pragma unroll
-            for (int b = 0; b < D - 1 - a; ++b) {
-                // adjacent compare-exchange (bubble network): stable, strict '>' keeps index order on ties
-                const bool sw = sv[b] > sv[b + 1];
-                const Real x = sw ? sv[b + 1] : sv[b], y = sw ? sv[b] : sv[b + 1];
-                const int ix = sw ? si[b + 1] : si[b], iy = sw ? si[b] : si[b + 1];
-                sv[b] = x; sv[b + 1] = y; si[b] = ix; si[b + 1] = iy;
-            }
-        Real left = limit, prev = (Real)0, amt[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            Real a = (sv[k] - prev) * limit;
-            if (a > left) a = left;
-            amt[k] = a; left -= a; prev = sv[k];
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            Real o = (Real)0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) o = (si[k] == i) ? amt[k] : o;
-            out[i] = o;
         }
     }
 }
 
 template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_>
-__device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_>::ship_cuts(const Real* v, int D, Real limit, Real* out) const {
-    if (D == F) ship_cuts_static<Real, F>(v, limit, out);
-    else if (D == W) ship_cuts_static<Real, W>(v, limit, out);
-    else ship_cuts_static<Real, R>(v, limit, out);
+template <class RawT>
+__device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_>::ship_cuts(const RawT* rv, int D, Real limit, Real* out) const {
+    if (D == F) ship_cuts_static<Real, RawT, F>(rv, limit, out);
+    else if (D == W) ship_cuts_static<Real, RawT, W>(rv, limit, out);
+    else ship_cuts_static<Real, RawT, R>(rv, limit, out);
 }
 
 // ---------------------------------------------------------------------------------
@@ -232,14 +229,16 @@ struct StaticActions {
     Philox4 blk; int blk_id;
     __device__ __forceinline__ StaticActions(const Io* row, RngKey k, unsigned long long g, unsigned ep, int tt)
         : rd(row), key(k), genv(g), episode(ep), t(tt), blk_id(-1) {}
-    __device__ __forceinline__ Real get(int idx) {
-        if constexpr (!RANDOM) return (Real)rd.get(idx);
+    using raw_t = Io;
+    __device__ __forceinline__ Io get_raw(int idx) {
+        if constexpr (!RANDOM) return rd.get(idx);
         else {
             const int b = idx >> 2;
             if (b != blk_id) { blk = rng_block(key, genv, episode, (unsigned)t, STREAM_ACTION, (unsigned)b); blk_id = b; }
-            return (Real)action_from_word(pick_word(blk, idx & 3));
+            return (Io)action_from_word(pick_word(blk, idx & 3));
         }
     }
+    __device__ __forceinline__ Real get(int idx) { return (Real)get_raw(idx); }
 };
 
 template <int L> struct ConstLeadtime { __device__ __forceinline__ constexpr int get(int) const { return L; } };
