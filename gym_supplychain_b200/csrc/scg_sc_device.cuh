@@ -124,7 +124,8 @@ __device__ __forceinline__ float action_from_word(unsigned w) { return (float)(i
 // arithmetic helpers that differ between the exact fp64 path and the fp32 path
 // ---------------------------------------------------------------------------------
 template <class Real> __device__ __forceinline__ Real denorm_action(Real a);
-template <> __device__ __forceinline__ double denorm_action<double>(double a) { return (a + 1.0) / 2.0; }   // :697-698
+// (a+1)/2 (:697-698).  fma(a, .5, .5) rounds (a+1)/2 once; halving is exact, so it equals fl(a+1)/2 bit for bit.
+template <> __device__ __forceinline__ double denorm_action<double>(double a) { return fma(a, 0.5, 0.5); }
 template <> __device__ __forceinline__ float denorm_action<float>(float a) { return fmaf(a, 0.5f, 0.5f); }
 
 template <class Real> __device__ __forceinline__ Real clamp_pm1(Real x) {
@@ -367,8 +368,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 // The reference skips the whole block when stock <= 0 (:283).  The compile-time kernels run it with
                 // limit = 0 instead (every amount 0, nothing pushed, costs += 0): same result, no divergent branch.
                 if (Tp::kStatic || s > (Real)0) {
-                    const Real c = tp.cap(n, p);
-                    Real limit = c < s ? c : s;
+                    // limit = min(stock_capacity, stock) (:61-65) is just the stock: it was clipped to the capacity above
+                    Real limit = s;
                     if (Tp::kStatic) limit = limit > (Real)0 ? limit : (Real)0;
                     Real out[MAXD], send[MAXD];
                     tp.ship_cuts(rv, D, limit, out);
