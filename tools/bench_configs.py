@@ -44,7 +44,9 @@ def emit(case, n, T, ms, bytes_per_step, **extra):
 
 
 def rollout_case(case, env_id, n, T, mode, iters, in_kernel_actions=False, **kw):
-    env = gsc.make(env_id, num_envs=n, mode=mode, seed=0, auto_reset=True, **kw)
+    if "beergame" not in env_id:
+        kw = dict(kw, mode=mode)
+    env = gsc.make(env_id, num_envs=n, seed=0, auto_reset=True, **kw)
     env.reset()
     A, O = env.n_actions, env.n_obs
     es = 4
@@ -104,12 +106,14 @@ def step_api_case(n, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--skip-sc", action="store_true")
     args = ap.parse_args()
     it = 3 if args.quick else 10
     torch.cuda.set_device(0)
-    step_api_case(65536, it)
     M = 1 << 20
-    for mode in ("mixed", "fast_f32"):
+    if not args.skip_sc:
+        step_api_case(65536, it)
+    for mode in (() if args.skip_sc else ("mixed", "fast_f32")):
         rollout_case("C3 2perstage 1M envs, fused 128-period rollout", "supplychain-2perstage-v0", M, 128, mode, it)
         rollout_case("C3 2perstage 1M envs, fused 128-period rollout", "supplychain-2perstage-v0", M, 128, mode, it,
                      in_kernel_actions=True)
