@@ -9,7 +9,8 @@ LIB_PATH = os.path.join(HERE, "libscg.so")
 
 MODE_FAST_F32, MODE_FAST_F64, MODE_EXACT_F64, MODE_MIXED = 0, 1, 2, 3
 MODES = {"fast_f32": MODE_FAST_F32, "fast_f64": MODE_FAST_F64, "exact_f64": MODE_EXACT_F64, "mixed": MODE_MIXED}
-FLAG_FORCE_GENERIC = 1
+FLAG_FORCE_GENERIC, FLAG_BUILD_INFO = 1, 2
+INFO_KEYS = ("stock", "stock_pen", "supply", "process", "process_pen", "ship", "ship_pen", "unmet_dem")
 DEMAND_UNIFORM, DEMAND_NORMAL, DEMAND_SIN_NORMAL, DEMAND_SIN_UNIFORM = 0, 1, 2, 3
 
 
@@ -52,7 +53,7 @@ class ScgInfo(C.Structure):
     _fields_ = [("n_envs", C.c_int64), ("family", C.c_int32), ("mode", C.c_int32), ("n_actions", C.c_int32),
                 ("n_obs", C.c_int32), ("n_demands", C.c_int32), ("n_leadtimes", C.c_int32),
                 ("total_time_steps", C.c_int32), ("elem_size", C.c_int32), ("ring_depth", C.c_int32),
-                ("heap_capacity", C.c_int32), ("kernel_variant", C.c_int32), ("reserved", C.c_int32),
+                ("heap_capacity", C.c_int32), ("kernel_variant", C.c_int32), ("info_values", C.c_int32),
                 ("state_bytes", C.c_int64)]
 
 
@@ -76,6 +77,7 @@ PROTOTYPES = [
     ("scg_get_state", C.c_int, [_vp, _vp, _vp]),
     ("scg_set_state", C.c_int, [_vp, _vp, _vp]),
     ("scg_return_stats", C.c_int, [_vp, _vp, C.c_int32, _vp]),
+    ("scg_get_info", C.c_int, [_vp, _vp, _vp]),
     ("scg_state_layout", C.c_int, [_vp, C.POINTER(C.c_int64 * 8)]),
     ("scg_launch_count", C.c_int64, [_vp]),
 ]

@@ -52,6 +52,7 @@ struct ScgEnv {
     size_t state_bytes = 0;
     int64_t layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double* stats = nullptr;        // [5] live  + [5] init pattern
+    double* info_buf = nullptr;     // build_info: [16*P][n]
     const int32_t* inj_demand = nullptr;
     const int32_t* inj_leadtimes = nullptr;
     // staging for *_host calls
@@ -189,6 +190,10 @@ static bool is_f64(int mode) { return mode != SCG_MODE_FAST_F32; }
 static int sc_alloc_state(ScgEnv* h) {
     const ScHostSpec& hs = h->hs;
     const size_t n = (size_t)h->opt.n_envs;
+    if (h->opt.flags & SCG_FLAG_BUILD_INFO) {
+        SCG_CUDA(cudaMalloc(&h->info_buf, (size_t)16 * hs.P * n * sizeof(double)));
+        SCG_CUDA(cudaMemset(h->info_buf, 0, (size_t)16 * hs.P * n * sizeof(double)));
+    }
     const size_t NP = (size_t)hs.N * hs.P;
     const bool exact = h->opt.mode == SCG_MODE_EXACT_F64;
     const size_t rs = is_f64(h->opt.mode) ? 8 : 4;
@@ -212,13 +217,13 @@ static int sc_alloc_state(ScgEnv* h) {
         s.n = (long long)n; s.t = (int*)(b + o_t); s.episode = (int*)(b + o_ep); s.ep_ret = (double*)(b + o_ret);
         s.stock = (double*)(b + o_stock); s.slot = (double*)(b + o_slot);
         s.hlen = (int*)(b + o_hlen); s.htime = (int*)(b + o_htime); s.hamt = (double*)(b + o_hamt);
-        s.stats = h->stats;
+        s.stats = h->stats; s.info = h->info_buf;
     } else {
         ScState<float>& s = h->st32;
         s.n = (long long)n; s.t = (int*)(b + o_t); s.episode = (int*)(b + o_ep); s.ep_ret = (double*)(b + o_ret);
         s.stock = (float*)(b + o_stock); s.slot = (float*)(b + o_slot);
         s.hlen = nullptr; s.htime = nullptr; s.hamt = nullptr;
-        s.stats = h->stats;
+        s.stats = h->stats; s.info = h->info_buf;
     }
     // episode = -1 so that the first reset starts episode 0
     SCG_CUDA(cudaMemset(b + o_ep, 0xFF, n * 4));
@@ -304,11 +309,12 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     h->variant = opt->mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(h->hs)
                : opt->mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(h->hs)
                : opt->mode == SCG_MODE_MIXED ? sc_match_variant_mixed(h->hs) : 0;
-    if (opt->flags & SCG_FLAG_FORCE_GENERIC) h->variant = 0;
+    if (opt->flags & (SCG_FLAG_FORCE_GENERIC | SCG_FLAG_BUILD_INFO)) h->variant = 0;
     ScgInfo& I = h->info;
     I.n_envs = opt->n_envs; I.family = 0; I.mode = opt->mode; I.n_actions = h->hs.A; I.n_obs = h->hs.O;
     I.n_demands = h->hs.RP; I.n_leadtimes = h->hs.K; I.total_time_steps = h->hs.T; I.elem_size = (is_f64(opt->mode) && opt->mode != SCG_MODE_MIXED) ? 8 : 4;
     I.ring_depth = h->hs.ring; I.heap_capacity = h->hs.heapcap; I.kernel_variant = h->variant; I.state_bytes = (int64_t)h->state_bytes;
+    I.info_values = (opt->flags & SCG_FLAG_BUILD_INFO) ? 16 * h->hs.P : 0;
     rc = dispatch(h, SC_OP_RESET, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc == SCG_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { set_error("initial reset failed: %s", cudaGetErrorString(e)); rc = SCG_ECUDA; } }
     if (rc != SCG_OK) { scg_destroy(h); return rc; }
@@ -399,7 +405,7 @@ void scg_destroy(ScgHandle h) {
         if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
-    cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
+    cudaFree(h->info_buf); cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
     delete h;
 }
 
@@ -568,6 +574,17 @@ int scg_return_stats(ScgHandle h, double* out, int32_t clear, void* stream) {
     if (rc != SCG_OK) return rc;
     SCG_CUDA(cudaMemcpyAsync(out, h->stats, 5 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     if (clear) SCG_CUDA(cudaMemcpyAsync(h->stats, h->stats + 5, 5 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SCG_OK;
+}
+
+int scg_get_info(ScgHandle h, double* out, void* stream) {
+    if (check_handle(h) != SCG_OK) return SCG_EINVAL;
+    if (!out) { set_error("null out"); return SCG_EINVAL; }
+    if (!h->info_buf) { set_error("handle was not created with SCG_FLAG_BUILD_INFO"); return SCG_ESTATE; }
+    int rc = set_device(h);
+    if (rc != SCG_OK) return rc;
+    SCG_CUDA(cudaMemcpyAsync(out, h->info_buf, (size_t)16 * h->hs.P * (size_t)h->opt.n_envs * sizeof(double),
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return SCG_OK;
 }
 

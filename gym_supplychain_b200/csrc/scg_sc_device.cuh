@@ -48,6 +48,7 @@ struct ScDevSpec {
     const int* ibeg;        // [N*P+1]
     const int* itime;       // [n_init]
     const Real* iamt;       // [n_init]
+    const unsigned long long* lt_thr;   // [maxL] stochastic lead times: lt = 1 + #{j < maxL-1 : word >= lt_thr[j]}
     const int* dkind;       // [P]
     const double *dlo, *dhi, *dstd, *dpeaks, *dminavg, *dmaxavg;   // [P]
 };
@@ -74,6 +75,7 @@ struct ScState {
     int* htime;        // EXACT: [N*P*heapcap][n]
     double* hamt;      // EXACT: [N*P*heapcap][n]
     double* stats;     // [5] count, sum, sumsq, min, max of finished-episode returns
+    double* info;      // build_info: [16*P][n] cumulative costs (8 keys x P) then units (8 keys x P); else nullptr
 };
 
 // ---------------------------------------------------------------------------------
@@ -114,7 +116,10 @@ __device__ __forceinline__ int sc_leadtime(const ScDevSpec<Real>& sp, const ScIn
     if (in.inj_leadtimes) return in.inj_leadtimes[((long long)(t - 1) * sp.K + k) * n_envs + env];
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
     Philox4 b = rng_block(in.key, genv, episode, (unsigned)t, STREAM_LEADTIME, (unsigned)(k >> 2));
-    return leadtime_from(pick_word(b, k & 3), (double)(sp.avgL - 1), sp.maxL);
+    const unsigned long long word = pick_word(b, k & 3);
+    int lt = 1;                                      // 1 + Poisson(avg-1) clipped to maxL, by inverse CDF (:670-672)
+    for (int q = 0; q + 1 < sp.maxL; ++q) lt += (word >= sp.lt_thr[q]) ? 1 : 0;
+    return lt;
 }
 
 // uniform action in [-1, 1) from one Philox word; the float value is what every mode sees
@@ -300,13 +305,36 @@ __device__ __forceinline__ void ship_cuts_dyn(const Real* v, int D, Real limit, 
 }
 
 // ---------------------------------------------------------------------------------
+// build_info statistics (supplychain_env.py:214-218 per node, :750-760 cumulative): 8 keys x P products of
+// costs and of units.  Key order = the reference's dict order.
+// ---------------------------------------------------------------------------------
+enum : int { INFO_STOCK = 0, INFO_STOCK_PEN = 1, INFO_SUPPLY = 2, INFO_PROCESS = 3, INFO_PROCESS_PEN = 4, INFO_SHIP = 5,
+             INFO_SHIP_PEN = 6, INFO_UNMET = 7 };
+
+struct NoInfo {
+    static constexpr bool kOn = false;
+    template <class R> __device__ __forceinline__ void add(int, int, R, R) const {}
+};
+struct GlobalInfo {                       // env-minor cumulative arrays; node order = accumulation order of the reference
+    static constexpr bool kOn = true;
+    double* base; long long n; int P;
+    template <class R> __device__ __forceinline__ void add(int key, int p, R cost, R units) const {
+        base[(long long)(key * P + p) * n] += (double)cost;
+        base[(long long)((8 + key) * P + p) * n] += (double)units;
+    }
+    __device__ __forceinline__ void clear() const {
+        for (int i = 0; i < 16 * P; ++i) base[(long long)i * n] = 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------------
 // One period for all nodes of one env.  Returns the total cost (reward = -cost).
 //   Ar: action reader  Real get(int idx)   (raw action in [-1,1])
 //   Lr: lead-time reader  int get(int k)
 //   Dr: demand reader  int cur(int rp, int p)   (row t-1)
 // ---------------------------------------------------------------------------------
-template <class Real, class Tp, class Pp, class Ar, class Lr, class Dr>
-__device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& ar, Lr& lr, Dr& dr) {
+template <class Real, class Tp, class Pp, class Ar, class Lr, class Dr, class Inf = NoInfo>
+__device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& ar, Lr& lr, Dr& dr, const Inf& inf = Inf()) {
     constexpr int MAXD = Tp::kMaxD;
     const int N = tp.N(), P = tp.P();
     if (Pp::kTwoPhase) {
@@ -329,7 +357,12 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
             Real s = pp.get_stock(np);
             if (!Pp::kTwoPhase) s = s + pp.arrive(np, t);
             const Real c = tp.cap(n, p);
-            if (s > c) { cost += tp.c_xstock() * (s - c); s = c; }
+            if (s > c) {
+                const Real pen = tp.c_xstock() * (s - c);
+                cost += pen;
+                inf.add(INFO_STOCK_PEN, p, pen, s - c);
+                s = c;
+            }
             pp.set_stock(np, s);
         }
         int ai = tp.act_off(n);
@@ -342,7 +375,9 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     const Real amount = denorm_action<Real>(ar.get(ai)) * tp.sup_cap(n, p);
                     ++ai;
                     if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
-                    cost += amount * tp.sup_cost(n, p);
+                    const Real sup = amount * tp.sup_cost(n, p);
+                    cost += sup;
+                    inf.add(INFO_SUPPLY, p, sup, amount);
                 }
             }
         }
@@ -399,7 +434,11 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) leaving += out[i];           // :331
                     pp.set_stock(np, s - leaving);
-                    if (factory) cost += leaving * tp.proc_cost(n, p);       // :338
+                    if (factory) {                                           // :338
+                        const Real pc = leaving * tp.proc_cost(n, p);
+                        cost += pc;
+                        inf.add(INFO_PROCESS, p, pc, leaving);
+                    }
                     Real sc = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {
@@ -407,9 +446,17 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                         sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
                     }
                     cost += sc;
+                    if constexpr (Inf::kOn) {
+                        Real shipped = (Real)0;                              // sum(amounts_to_ship), :356
+                        for (int i = 0; i < D; ++i) shipped += send[i];
+                        inf.add(INFO_SHIP, p, sc, shipped);
+                    }
                 }
-                cost += tp.c_xproc() * over_proc;                            // :361
-                cost += tp.c_xship() * over_ship;                            // :366
+                const Real ppen = tp.c_xproc() * over_proc, spen = tp.c_xship() * over_ship;
+                cost += ppen;                                                // :361
+                cost += spen;                                                // :366
+                inf.add(INFO_PROCESS_PEN, p, ppen, over_proc);
+                inf.add(INFO_SHIP_PEN, p, spen, over_ship);
                 ai += D;
             }
         } else {
@@ -422,12 +469,18 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 const Real s = pp.get_stock(np);
                 const Real served = s < d ? s : d;
                 pp.set_stock(np, s - served);
-                cost += tp.c_unmet() * (d - served);
+                const Real lost = tp.c_unmet() * (d - served);
+                cost += lost;
+                inf.add(INFO_UNMET, p, lost, d - served);
             }
         }
         // 6. holding cost (:390-391)
 #pragma unroll(Tp::kStatic ? 8 : 1)
-        for (int p = 0; p < P; ++p) cost += pp.get_stock(n * P + p) * tp.hold(n, p);
+        for (int p = 0; p < P; ++p) {
+            const Real held = pp.get_stock(n * P + p), hc = held * tp.hold(n, p);
+            cost += hc;
+            inf.add(INFO_STOCK, p, hc, held);
+        }
         total += cost;
     }
     return total;
@@ -559,7 +612,7 @@ __device__ __forceinline__ void sc_write_obs(const DynTopoOps<Real>& tp, const S
     else sc_obs_ring<Real>(tp, sp, pp, t, dr, ow);
 }
 
-template <class Real, class Io, int MODE>
+template <class Real, class Io, int MODE, bool INFO>
 __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                                                          const unsigned char* __restrict__ reset_mask, int do_reset,
                                                          const Io* __restrict__ actions, Io* __restrict__ obs,
@@ -573,9 +626,11 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
         int t = st.t[env];
         unsigned episode = (unsigned)st.episode[env];
         double ep_ret = st.ep_ret[env];
+        GlobalInfo ginf{INFO ? st.info + env : nullptr, st.n, sp.P};
         if (do_reset && (reset_mask == nullptr || reset_mask[env])) {
             ++episode; t = 0; ep_ret = 0.0;
             pp.reset(tp, sp);
+            if constexpr (INFO) ginf.clear();
         }
         if (n_steps == 0) {       // reset(): emit the current observation
             DynDemand<Real> dr{sp, in, st.n, env, episode, t};
@@ -596,7 +651,9 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
                                    (unsigned long long)(in.first_env + env), episode, t, Philox4{0, 0, 0, 0}, -1};
             DynLeadtimes<Real> lr{sp, in, st.n, env, episode, t};
             DynDemand<Real> dr{sp, in, st.n, env, episode, t};
-            const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr);
+            Real cost;
+            if constexpr (INFO) cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr, ginf);
+            else cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr);
             const Real r = -cost;
             ep_ret += (double)r;
             const bool fin = (t == sp.T);
@@ -605,6 +662,7 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
                 if (in.auto_reset) {
                     ++episode; t = 0; ep_ret = 0.0;
                     pp.reset(tp, sp);
+                    if constexpr (INFO) ginf.clear();
                     dr.episode = episode; dr.t = 0;
                 }
             }

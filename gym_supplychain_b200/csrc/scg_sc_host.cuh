@@ -1,12 +1,28 @@
 // scg_sc_host.cuh -- host-side launch logic for the supply-chain kernels, templated on Real.
 // Included by scg_sc_f32.cu (default FMA contraction) and scg_sc_f64.cu (-fmad=false).
 #pragma once
+#include <cmath>
 #include <cstring>
 
 #include "scg_internal.h"
 #include "scg_sc_static.cuh"
 
 namespace scg {
+
+// Integer thresholds of the truncated-Poisson lead-time draw: with u = word / 2^32,
+// lt = 1 + #{j < maxL-1 : u >= CDF_Poisson(avg-1)(j)}  <=>  word >= ceil(CDF(j) * 2^32)   (supplychain_env.py:670-672)
+static inline std::vector<unsigned long long> sc_leadtime_thresholds(const ScHostSpec& hs) {
+    std::vector<unsigned long long> thr((size_t)(hs.maxL > 1 ? hs.maxL : 1), ~0ull);
+    const double lam = (double)(hs.avgL - 1);
+    double p = std::exp(-lam), F = p;
+    for (int j = 0; j + 1 < hs.maxL; ++j) {
+        const double x = std::ceil(F * 4294967296.0);
+        thr[j] = x >= 4294967296.0 ? (1ull << 32) : (unsigned long long)x;      // 2^32: never reached by a 32-bit word
+        p *= lam / (double)(j + 1);
+        F += p;
+    }
+    return thr;
+}
 
 // ---- device spec ---------------------------------------------------------------
 template <class Real>
@@ -34,6 +50,8 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
     size_t o_ibeg = put_int(hs.ibeg), o_itime = put_int(hs.itime), o_iamt = put_real(hs.iamt), o_dkind = put_int(hs.dkind);
     size_t o_dlo = put_dbl(hs.dlo), o_dhi = put_dbl(hs.dhi), o_dstd = put_dbl(hs.dstd), o_dpk = put_dbl(hs.dpeaks);
     size_t o_dmin = put_dbl(hs.dminavg), o_dmax = put_dbl(hs.dmaxavg);
+    const std::vector<unsigned long long> thr = sc_leadtime_thresholds(hs);
+    size_t o_thr = put(thr.data(), thr.size() * sizeof(unsigned long long));
 
     unsigned char* d = nullptr;
     SCG_CUDA(cudaMalloc(&d, buf.size()));
@@ -53,6 +71,7 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
     sp.ibeg = SCG_P(int, o_ibeg); sp.itime = SCG_P(int, o_itime); sp.iamt = SCG_P(Real, o_iamt); sp.dkind = SCG_P(int, o_dkind);
     sp.dlo = SCG_P(double, o_dlo); sp.dhi = SCG_P(double, o_dhi); sp.dstd = SCG_P(double, o_dstd); sp.dpeaks = SCG_P(double, o_dpk);
     sp.dminavg = SCG_P(double, o_dmin); sp.dmaxavg = SCG_P(double, o_dmax);
+    sp.lt_thr = SCG_P(unsigned long long, o_thr);
 #undef SCG_P
     memcpy(devspec_out, &sp, sizeof(sp));
     *blob_out = d;
@@ -60,8 +79,9 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
 }
 
 // ---- layered-variant matching ----------------------------------------------------
-static inline bool sc_is_layered(const ScHostSpec& hs, int S, int F, int W, int R, int P, int L) {
-    if (hs.N != S + F + W + R || hs.P != P || hs.stochL || hs.avgL != L || hs.maxL != L || hs.ring != L) return false;
+static inline bool sc_is_layered(const ScHostSpec& hs, int S, int F, int W, int R, int P, int L, int ML = 0, bool stoch = false) {
+    if (ML == 0) ML = L;
+    if (hs.N != S + F + W + R || hs.P != P || (hs.stochL != 0) != stoch || hs.avgL != L || hs.maxL != ML || hs.ring != ML) return false;
     const int cnt[4] = {S, F, W, R};
     const int base[4] = {0, S, S + F, S + F + W};
     for (int e = 0; e < 4; ++e)
@@ -84,8 +104,8 @@ static inline bool sc_is_layered(const ScHostSpec& hs, int S, int F, int W, int 
     return true;
 }
 
-template <class Real, int S, int F, int W, int R, int P, int L>
-static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R, P, L>& c) {
+template <class Real, int S, int F, int W, int R, int P, int L, int ML, bool STOCH>
+static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>& c) {
     memset(&c, 0, sizeof(c));
     constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
     for (int i = 0; i < NP; ++i) {
@@ -94,7 +114,7 @@ static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R,
         c.obs_stock[i] = (float)(1.0 / hs.cap[i]);
         c.obs_mid[i] = (float)(1.0 / hs.max_ship[i]);
         c.obs_last[i] = (float)(1.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
-        for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) c.init_slot[i * L + hs.itime[k] - 1] += (Real)hs.iamt[k];
+        for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) c.init_slot[i * ML + hs.itime[k] - 1] += (Real)hs.iamt[k];
     }
     for (int i = 0; i < S * P; ++i) { c.sup_cap[i] = (Real)hs.sup_cap[i]; c.sup_cost[i] = (Real)hs.sup_cost[i]; }
     for (int j = 0; j < F; ++j) {
@@ -117,17 +137,19 @@ static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R,
         c.dlo_i[p] = (int)hs.dlo[p]; c.dcount[p] = (int)hs.dhi[p] - (int)hs.dlo[p] + 1;
         if (hs.dkind[p] != 0) c.all_uniform = 0;
     }
+    const std::vector<unsigned long long> thr = sc_leadtime_thresholds(hs);
+    for (int j = 0; j < ML; ++j) c.lt_thr[j] = j < (int)thr.size() ? thr[j] : ~0ull;
     c.T = hs.T;
     c.obs_time = (float)(1.0 / (double)hs.T);
 }
 
-template <class Real, class Io, int S, int F, int W, int R, int P, int L, int THREADS, int MINB>
+template <class Real, class Io, int S, int F, int W, int R, int P, int L, int THREADS, int MINB, int ML = L, bool STOCH = false>
 static int sc_launch_layered(const ScRun& r) {
-    using C = LayeredConsts<Real, S, F, W, R, P, L>;
-    using Tp = LayeredTopo<Real, sizeof(Io) == 8, S, F, W, R, P, L>;
+    using C = LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>;
+    using Tp = LayeredTopo<Real, sizeof(Io) == 8, S, F, W, R, P, L, ML, STOCH>;
     static_assert(sizeof(C) <= 3800, "constants must fit the kernel parameter bank");
     C c;
-    sc_fill_consts<Real, S, F, W, R, P, L>(*r.hs, c);
+    sc_fill_consts<Real, S, F, W, R, P, L, ML, STOCH>(*r.hs, c);
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
@@ -135,11 +157,11 @@ static int sc_launch_layered(const ScRun& r) {
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
     if (r.actions == nullptr) {
-        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, true, THREADS, MINB>;
+        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, ML, STOCH, true, THREADS, MINB>;
         SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, nullptr, (Io*)r.obs, (Io*)r.reward, r.done);
     } else {
-        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, false, THREADS, MINB>;
+        auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, ML, STOCH, false, THREADS, MINB>;
         SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
     }
@@ -160,15 +182,23 @@ static int sc_launch_generic(const ScRun& r) {
         // only the -fmad=false translation unit (Real = Io = double) may instantiate the exact kernel:
         // a second copy compiled with FMA contraction would be an ODR clash and break bit-exactness
         if constexpr (sizeof(Real) == 8 && sizeof(Io) == 8) {
-            sc_generic_kernel<double, double, 1><<<blocks, threads, 0, r.stream>>>(
-                sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
+            if (st.info)
+                sc_generic_kernel<double, double, 1, true><<<blocks, threads, 0, r.stream>>>(
+                    sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
+            else
+                sc_generic_kernel<double, double, 1, false><<<blocks, threads, 0, r.stream>>>(
+                    sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
         } else {
             set_error("EXACT mode needs the fp64 translation unit");
             return SCG_EINVAL;
         }
     } else {
-        sc_generic_kernel<Real, Io, 0><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
-                                                                           (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
+        if (st.info)
+            sc_generic_kernel<Real, Io, 0, true><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
+                                                                                     (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
+        else
+            sc_generic_kernel<Real, Io, 0, false><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
+                                                                                      (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
     }
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;

@@ -15,6 +15,7 @@ int sc_match_variant_mixed(const ScHostSpec& hs) {
     if (sc_is_layered(hs, 3, 3, 3, 3, 2, 2)) return 3;
     if (sc_is_layered(hs, 1, 1, 1, 3, 1, 2)) return 4;
     if (sc_is_layered(hs, 2, 2, 2, 2, 2, 2)) return 5;
+    if (sc_is_layered(hs, 2, 2, 2, 2, 1, 2, 4, true)) return 6;   // stochastic lead times avg 2 / max 4 (supplychain-v0 demo chain)
     return 0;
 }
 
@@ -26,6 +27,7 @@ int sc_run_mixed(const ScRun& r) {
             case 3: return sc_launch_layered<double, float, 3, 3, 3, 3, 2, 2, 64, 4>(r);
             case 4: return sc_launch_layered<double, float, 1, 1, 1, 3, 1, 2, 128, 3>(r);
             case 5: return sc_launch_layered<double, float, 2, 2, 2, 2, 2, 2, 64, 4>(r);
+            case 6: return sc_launch_layered<double, float, 2, 2, 2, 2, 1, 2, 128, 3, 4, true>(r);
             default: break;
         }
     }

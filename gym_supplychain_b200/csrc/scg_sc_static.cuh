@@ -17,10 +17,12 @@
 
 namespace scg {
 
-template <class Real, int S, int F, int W, int R, int P, int L>
+// L = avg_leadtime (constant lead time when !STOCH; number of obs buckets), ML = max_leadtime = ring depth.
+template <class Real, int S, int F, int W, int R, int P, int L, int ML, bool STOCH>
 struct LayeredConsts {
     static constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
-    Real cap[NP], hold[NP], stock0[NP], max_ship[NP], init_slot[NP * L];
+    Real cap[NP], hold[NP], stock0[NP], max_ship[NP], init_slot[NP * ML];
+    unsigned long long lt_thr[ML];                       // stochastic lead times: lt = 1 + #{j < ML-1 : word >= lt_thr[j]}
     float obs_stock[NP], obs_mid[NP], obs_last[NP];      // 1/cap, 1/max_ship, 1/(max_ship*(maxL-avgL+1)) (non-exact obs path)
     Real sup_cap[S * P], sup_cost[S * P];
     Real proc_cap[F], ratio[F * P], inv_ratio[F * P], proc_cost[F * P];
@@ -36,14 +38,15 @@ struct LayeredConsts {
 
 // EXACT = true keeps IEEE divisions (fp64 I/O modes: obs/rewards comparable bit-for-bit with the generic
 // fp64 kernel); false multiplies by host-computed reciprocals (fp32 and mixed modes).
-template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_>
+template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_, int ML_, bool STOCH_>
 struct LayeredTopo {
-    using C = LayeredConsts<Real, S, F, W, R, P_, L_>;
+    using C = LayeredConsts<Real, S, F, W, R, P_, L_, ML_, STOCH_>;
     static constexpr bool kStatic = true;
-    static constexpr int kN = S + F + W + R, kP = P_, kL = L_;
+    static constexpr int kN = S + F + W + R, kP = P_, kL = L_, kML = ML_;
+    static constexpr int kK = S * (P_ + F) + F * W + W * R;     // lead-time values per period (:597-605)
     static constexpr int kMaxD = (F > W ? (F > R ? F : R) : (W > R ? W : R));
     static constexpr int kA = S * (P_ + P_ * F) + F * P_ * W + W * P_ * R;
-    static constexpr int kO = R * P_ + kN * P_ * (1 + L_) + 1;
+    static constexpr int kO = R * P_ + kN * P_ * (1 + L_) + 1;   // (:617-621)
     static constexpr int kRP = R * P_;
     const C& c;
     __device__ __forceinline__ explicit LayeredTopo(const C& cc) : c(cc) {}
@@ -54,8 +57,8 @@ struct LayeredTopo {
     __device__ __forceinline__ constexpr int N() const { return kN; }
     __device__ __forceinline__ constexpr int P() const { return kP; }
     __device__ __forceinline__ constexpr int avgL() const { return kL; }
-    __device__ __forceinline__ constexpr int maxL() const { return kL; }
-    __device__ __forceinline__ constexpr int ring() const { return kL; }
+    __device__ __forceinline__ constexpr int maxL() const { return kML; }
+    __device__ __forceinline__ constexpr int ring() const { return kML; }
     __device__ __forceinline__ int T() const { return c.T; }
     __device__ __forceinline__ constexpr bool last(int n) const { return ech(n) == 3; }
     __device__ __forceinline__ constexpr bool supplier(int n) const { return ech(n) == 0; }
@@ -81,7 +84,10 @@ struct LayeredTopo {
                            : (ech(n) == 1 ? S * (kP + kP * F) + loc(n) * kP * W
                                           : (ech(n) == 2 ? S * (kP + kP * F) + F * kP * W + loc(n) * kP * R : kA));
     }
-    __device__ __forceinline__ constexpr int lt_off(int) const { return 0; }
+    __device__ __forceinline__ constexpr int lt_off(int n) const {       // n_supply + n_ship/P values per node (:719-722)
+        return ech(n) == 0 ? loc(n) * (kP + F)
+                           : (ech(n) == 1 ? S * (kP + F) + loc(n) * W : (ech(n) == 2 ? S * (kP + F) + F * W + loc(n) * R : kK));
+    }
     __device__ __forceinline__ constexpr int ret_idx(int n) const { return loc(n); }
     __device__ __forceinline__ Real c_unmet() const { return c.c_unmet; }
     __device__ __forceinline__ Real c_xstock() const { return c.c_xstock; }
@@ -157,9 +163,9 @@ __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real
     }
 }
 
-template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_>
+template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_, int ML_, bool STOCH_>
 template <class RawT>
-__device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_>::ship_cuts(const RawT* rv, int D, Real limit, Real* out) const {
+__device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_, ML_, STOCH_>::ship_cuts(const RawT* rv, int D, Real limit, Real* out) const {
     if (D == F) ship_cuts_static<Real, RawT, F>(rv, limit, out);
     else if (D == W) ship_cuts_static<Real, RawT, W>(rv, limit, out);
     else ship_cuts_static<Real, RawT, R>(rv, limit, out);
@@ -168,7 +174,7 @@ __device__ __forceinline__ void LayeredTopo<Real, EXACT, S, F, W, R, P_, L_>::sh
 // ---------------------------------------------------------------------------------
 // register-resident state
 // ---------------------------------------------------------------------------------
-template <class Real, int NP, int L>
+template <class Real, int NP, int L, bool STOCH>
 struct RingRegs {
     static constexpr bool kTwoPhase = true;
     static constexpr bool kExactObs = false;
@@ -184,7 +190,13 @@ struct RingRegs {
         slot[np * L + L - 1] = (Real)0;
         return a;
     }
-    __device__ __forceinline__ void push(int np, int, int /*lt == L*/, Real amount) { slot[np * L + L - 1] += amount; }
+    __device__ __forceinline__ void push(int np, int, int lt, Real amount) {
+        if constexpr (!STOCH) slot[np * L + L - 1] += amount;              // constant lead time == ring depth
+        else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) slot[np * L + k] += (lt - 1 == k) ? amount : (Real)0;
+        }
+    }
 };
 
 // Reads one env's row of LEN elements out of the warp tile, 16/8/4 bytes at a time.  All
@@ -242,6 +254,24 @@ struct StaticActions {
 };
 
 template <int L> struct ConstLeadtime { __device__ __forceinline__ constexpr int get(int) const { return L; } };
+
+// K lead times of one period packed 4 bits each (value - 1), so that the data-dependent cursor of
+// SC_Node.act (:252-254, F4b) can index them at run time without touching local memory.
+template <int K> struct PackedLeadtimes {
+    static constexpr int NW = (K + 15) / 16;
+    unsigned long long w[NW];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = 0ull;
+    }
+    __device__ __forceinline__ void set(int k, int lt) { w[k >> 4] |= (unsigned long long)(lt - 1) << ((k & 15) * 4); }   // k static
+    __device__ __forceinline__ int get(int k) const {
+        unsigned long long v = w[0];
+#pragma unroll
+        for (int i = 1; i < NW; ++i) v = ((k >> 4) == i) ? w[i] : v;
+        return (int)((v >> ((k & 15) * 4)) & 15ull) + 1;
+    }
+};
 
 template <int RP> struct RegDemand {
     int cur_[RP], next_[RP];
@@ -309,13 +339,14 @@ __device__ __forceinline__ void warp_copy(Real* __restrict__ dst, const Real* __
 // ---------------------------------------------------------------------------------
 // the fused rollout kernel
 // ---------------------------------------------------------------------------------
-template <class Real, class Io, int S, int F, int W, int R, int P, int L, bool RANDOM_ACT, int THREADS, int MINB>
+template <class Real, class Io, int S, int F, int W, int R, int P, int L, int ML, bool STOCH, bool RANDOM_ACT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L> c, ScDevSpec<Real> sp, ScState<Real> st,
+sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH> c, ScDevSpec<Real> sp, ScState<Real> st,
                    ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
                    Io* __restrict__ reward, unsigned char* __restrict__ done) {
     constexpr bool kExact = sizeof(Io) == 8;
-    using Tp = LayeredTopo<Real, kExact, S, F, W, R, P, L>;
+    using Tp = LayeredTopo<Real, kExact, S, F, W, R, P, L, ML, STOCH>;
+    constexpr int K = Tp::kK;
     constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -340,7 +371,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
 
-    RingRegs<Real, NP, L> pp;
+    RingRegs<Real, NP, ML, STOCH> pp;
     RegDemand<RP> dm;
     int t = 0; unsigned episode = 0; double ep_ret = 0.0;
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
@@ -372,7 +403,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
 #pragma unroll
         for (int i = 0; i < NP; ++i) pp.stock[i] = st.stock[(long long)i * n + env];
 #pragma unroll
-        for (int i = 0; i < NP * L; ++i) pp.slot[i] = st.slot[(long long)i * n + env];
+        for (int i = 0; i < NP * ML; ++i) pp.slot[i] = st.slot[(long long)i * n + env];
         fetch_next_demand(t);
     }
 
@@ -396,8 +427,37 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
 #pragma unroll
             for (int rp = 0; rp < RP; ++rp) dm.cur_[rp] = dm.next_[rp];
             StaticActions<Real, Io, RANDOM_ACT, A> ar(s_act + lane * A, in.key, genv, episode, t);
-            ConstLeadtime<L> lr;
-            const Real cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+            Real cost;
+            if constexpr (!STOCH) {
+                ConstLeadtime<L> lr;
+                cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+            } else {
+                // this period's K lead times: injected table, or 1 + Poisson(avg-1) clipped to ML by integer
+                // thresholds on one Philox word each (same words and thresholds as the generic kernel)
+                PackedLeadtimes<K> lr;
+                lr.clear();
+                if (in.inj_leadtimes != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) lr.set(k, in.inj_leadtimes[((long long)(t - 1) * K + k) * n + env]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < (K + 3) / 4; ++b) {
+                        const Philox4 blk = rng_block(in.key, genv, episode, (unsigned)t, STREAM_LEADTIME, (unsigned)b);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = 4 * b + j;
+                            if (k < K) {
+                                const unsigned long long word = pick_word(blk, j);
+                                int lt = 1;
+#pragma unroll
+                                for (int q = 0; q + 1 < ML; ++q) lt += (word >= c.lt_thr[q]) ? 1 : 0;
+                                lr.set(k, lt);
+                            }
+                        }
+                    }
+                }
+                cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+            }
             r = -cost;
             ep_ret += (double)r;
             fin = (t == c.T);
@@ -408,7 +468,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
 #pragma unroll
                     for (int i = 0; i < NP; ++i) pp.stock[i] = c.stock0[i];
 #pragma unroll
-                    for (int i = 0; i < NP * L; ++i) pp.slot[i] = c.init_slot[i];
+                    for (int i = 0; i < NP * ML; ++i) pp.slot[i] = c.init_slot[i];
                 }
             }
         }
@@ -448,11 +508,14 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
                         const int np = nn * P + p;
 #pragma unroll
                         for (int k = 0; k + 1 < L; ++k) {
-                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * L + k] / c.max_ship[np]));
-                            else ow.put(o++, unit((float)pp.slot[np * L + k], c.obs_mid[np]));
+                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * ML + k] / c.max_ship[np]));
+                            else ow.put(o++, unit((float)pp.slot[np * ML + k], c.obs_mid[np]));
                         }
-                        if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * L + L - 1] / (c.max_ship[np] * (Real)1)));
-                        else ow.put(o++, unit((float)pp.slot[np * L + L - 1], c.obs_last[np]));
+                        Real rest = (Real)0;                       // everything arriving at t+L or later
+#pragma unroll
+                        for (int k = L - 1; k < ML; ++k) rest += pp.slot[np * ML + k];
+                        if constexpr (kExact) ow.put(o++, obs_norm<Real>(rest / (c.max_ship[np] * (Real)(ML - (L - 1)))));
+                        else ow.put(o++, unit((float)rest, c.obs_last[np]));
                     }
                 }
                 if constexpr (kExact) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
@@ -478,7 +541,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L>
 #pragma unroll
         for (int i = 0; i < NP; ++i) st.stock[(long long)i * n + env] = pp.stock[i];
 #pragma unroll
-        for (int i = 0; i < NP * L; ++i) st.slot[(long long)i * n + env] = pp.slot[i];
+        for (int i = 0; i < NP * ML; ++i) st.slot[(long long)i * n + env] = pp.slot[i];
     }
     rs.flush(st.stats);
 }

@@ -40,7 +40,8 @@ class _ScgEnvBase(object):
     reward_range = (-float("inf"), float("inf"))
     spec = None
 
-    def _init_handle(self, create_fn, c_spec, num_envs, device, mode, auto_reset, seed, first_env, force_generic=False):
+    def _init_handle(self, create_fn, c_spec, num_envs, device, mode, auto_reset, seed, first_env, force_generic=False,
+                     build_info=False):
         torch = _torch()
         self._single = num_envs is None
         self.num_envs = 1 if num_envs is None else int(num_envs)
@@ -57,7 +58,8 @@ class _ScgEnvBase(object):
         opt.device = self.device.index
         opt.mode = _lib.MODES[mode]
         opt.auto_reset = 1 if auto_reset else 0
-        opt.flags = _lib.FLAG_FORCE_GENERIC if force_generic else 0
+        opt.flags = (_lib.FLAG_FORCE_GENERIC if force_generic else 0) | (_lib.FLAG_BUILD_INFO if build_info else 0)
+        self.build_info = bool(build_info)
         self.auto_reset = bool(auto_reset)
         self._lib = lib
         self._h = C.c_void_p()
@@ -178,9 +180,12 @@ class _ScgEnvBase(object):
         if self._single:
             a = np.asarray(action)
             obs, rew, done = self._step_tensors(a.reshape(1, -1))
-            return self._to_single_obs(obs), self._to_single_reward(rew), bool(done.item()), {}
+            return self._to_single_obs(obs), self._to_single_reward(rew), bool(done.item()), self._info()
         obs, rew, done = self._step_tensors(action)
-        return obs, rew, done, {}
+        return obs, rew, done, self._info()
+
+    def _info(self):
+        return {}
 
     def render(self, mode="human"):
         raise NotImplementedError("render() is out of scope of the B200 hot path (SURVEY.md C13)")
@@ -195,8 +200,6 @@ class SupplyChainEnv(_ScgEnvBase):
                  processing_ratio=3, stochastic_leadtimes=False, avg_leadtime=2, max_leadtime=2, total_time_steps=360,
                  seed=None, build_info=False, demand_perturb_norm=False,
                  num_envs=None, device=None, mode=None, auto_reset=None, first_env=0, force_generic=False):
-        if build_info:
-            raise NotImplementedError("build_info=True (info['sc_episode'] statistics) is not on the GPU path yet")
         self.flat = FlatSpec(nodes_info, num_products=num_products, unmet_demand_cost=unmet_demand_cost,
                              exceeded_stock_capacity_cost=exceeded_stock_capacity_cost,
                              exceeded_process_capacity_cost=exceeded_process_capacity_cost,
@@ -218,7 +221,7 @@ class SupplyChainEnv(_ScgEnvBase):
         torch = _torch()
         self._io_dtype = torch.float32 if mode in ("fast_f32", "mixed") else torch.float64
         self._init_handle(_lib.load().scg_sc_create, self.flat.c_struct(), num_envs, device, mode, auto_reset, seed, first_env,
-                          force_generic=force_generic)
+                          force_generic=force_generic, build_info=build_info)
         assert self.n_actions == self.flat.n_actions and self.n_obs == self.flat.n_obs
 
     def inject(self, demand=None, leadtimes=None):
@@ -246,6 +249,25 @@ class SupplyChainEnv(_ScgEnvBase):
 
     def _to_single_reward(self, rew):
         return float(rew[0].item())
+
+    def _info(self):
+        """info dict of step(): {} or, with build_info=True, {'sc_episode': {'rewards', 'costs', 'units'}} with the
+        reference's 8 keys (supplychain_env.py:684-695, :793-796).  Single env: python floats / lists per product;
+        vector env: tensors (rewards [N], each key [P, N])."""
+        if not self.build_info:
+            return {}
+        torch = _torch()
+        P, n = self.flat.P, self.num_envs
+        buf = torch.empty((16 * P, n), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.scg_get_info(self._h, self._ptr(buf), self._stream()))
+        rewards = self.state_dict()["ep_ret"].clone()
+        costs = {k: buf[i * P:(i + 1) * P] for i, k in enumerate(_lib.INFO_KEYS)}
+        units = {k: buf[(8 + i) * P:(9 + i) * P] for i, k in enumerate(_lib.INFO_KEYS)}
+        if self._single:
+            costs = {k: [float(x) for x in v[:, 0].tolist()] for k, v in costs.items()}
+            units = {k: [float(x) for x in v[:, 0].tolist()] for k, v in units.items()}
+            rewards = float(rewards[0])
+        return {"sc_episode": {"rewards": rewards, "costs": costs, "units": units}}
 
     def state_dict(self):
         """Decode the raw state blob (scg_state_layout): time step, episode, stocks [N,P,n] and either the

@@ -85,6 +85,8 @@ typedef struct ScgOptions {
 } ScgOptions;
 
 #define SCG_FLAG_FORCE_GENERIC 1   /* never pick a compile-time-topology kernel (tests / A-B timing)    */
+#define SCG_FLAG_BUILD_INFO    2   /* supply chain: keep the reference's build_info statistics (implies the  */
+                                   /* runtime-topology kernel); read them with scg_get_info                  */
 
 /* Flat description of a SupplyChainEnv (what supplychain_env.py:499-626 builds from
  * `nodes_info` + kwargs).  N nodes in act order, P products, E directed edges (CSR by source
@@ -157,7 +159,7 @@ typedef struct ScgInfo {
     int32_t ring_depth;        /* FAST modes: slots per (node, product)                      */
     int32_t heap_capacity;     /* EXACT mode: entries per (node, product) queue              */
     int32_t kernel_variant;    /* 0 generic runtime-topology kernel, >0 a compile-time one   */
-    int32_t reserved;
+    int32_t info_values;       /* 16*P when SCG_FLAG_BUILD_INFO, else 0                      */
     int64_t state_bytes;       /* size of the blob for scg_get_state / scg_set_state         */
 } ScgInfo;
 
@@ -206,6 +208,12 @@ SCG_API int  scg_set_state(ScgHandle h, const void* blob, void* stream);
  * out[5] = {count, sum, sum of squares, min, max} as doubles (device pointer; the values a
  * multi-GPU caller all-reduces: SUM on the first three, MIN, MAX).  clear != 0 zeroes them after. */
 SCG_API int  scg_return_stats(ScgHandle h, double* out, int32_t clear, void* stream);
+
+/* build_info statistics of the current episode (supplychain_env.py:684-695, :750-760, :793-796):
+ * out = double[16*P][n_envs] (device pointer), rows 0..8P-1 cumulative costs and rows 8P..16P-1 cumulative units,
+ * key-major then product, keys in the reference's order: stock, stock_pen, supply, process, process_pen, ship,
+ * ship_pen, unmet_dem.  The cumulative reward ('rewards') is ep_ret in the state blob.  Needs SCG_FLAG_BUILD_INFO. */
+SCG_API int  scg_get_info(ScgHandle h, double* out, void* stream);
 
 /* Byte offsets of the arrays inside the state blob (all env-minor: element i of env e at [i*n_envs + e]).
  * supply chain: {ep_ret f64[n], heap_amount f64[NP*cap*n], stock Real[NP*n], slot Real[NP*ring*n],

@@ -66,9 +66,9 @@ def run_supplychain_case(name, cls_name, kwargs, episodes=1, seed=0, style="mixe
     SupplyChainEnv.__init__ = spy
     try:
         if cls_name == "SupplyChainEnv":
-            env = SupplyChainEnv(kwargs["nodes_info"], **{k: v for k, v in kwargs.items() if k != "nodes_info"})
+            env = SupplyChainEnv(kwargs["nodes_info"], build_info=True, **{k: v for k, v in kwargs.items() if k != "nodes_info"})
         else:
-            env = getattr(E, cls_name)(**kwargs)
+            env = getattr(E, cls_name)(build_info=True, **kwargs)     # info['sc_episode'] is recorded; dynamics unchanged
     finally:
         SupplyChainEnv.__init__ = orig_init
 
@@ -86,7 +86,8 @@ def run_supplychain_case(name, cls_name, kwargs, episodes=1, seed=0, style="mixe
             heap_cap = max(heap_cap, n_src * env.max_leadtime + n_init)
 
     rec = {k: [] for k in ("demand", "leadtimes", "actions", "obs", "reward", "done", "stock",
-                           "heap_len", "heap_time", "heap_amount")}
+                           "heap_len", "heap_time", "heap_amount", "info_costs", "info_units", "info_rewards")}
+    KEYS = ("stock", "stock_pen", "supply", "process", "process_pen", "ship", "ship_pen", "unmet_dem")
 
     def snapshot():
         st = np.zeros((N, P))
@@ -120,7 +121,11 @@ def run_supplychain_case(name, cls_name, kwargs, episodes=1, seed=0, style="mixe
         done = False
         while not done:
             a = make_actions(rs, A, style)
-            obs, r, done, _ = env.step(a)
+            obs, r, done, info = env.step(a)
+            ep = info["sc_episode"]
+            e["info_costs"].append(np.array([[float(ep["costs"][k][p]) for p in range(P)] for k in KEYS]))
+            e["info_units"].append(np.array([[float(ep["units"][k][p]) for p in range(P)] for k in KEYS]))
+            e["info_rewards"].append(float(ep["rewards"]))
             st, hl, ht, ha = snapshot()
             e["actions"].append(a)
             e["obs"].append(np.asarray(obs, dtype=np.float64))
@@ -129,6 +134,7 @@ def run_supplychain_case(name, cls_name, kwargs, episodes=1, seed=0, style="mixe
         for k in rec:
             rec[k].append(np.asarray(e[k]))
 
+    captured["kwargs"].pop("build_info", None)
     meta = {"name": name, "cls": cls_name, "ctor_kwargs": _jsonable(kwargs), "nodes_info": captured["nodes_info"],
             "env_kwargs": _jsonable(captured["kwargs"]), "N": N, "P": P, "T": T, "A": A, "O": O, "R": R,
             "K": int(getattr(env, "count_leadtimes_per_timestep", 0)), "heap_cap": int(heap_cap),

@@ -35,7 +35,10 @@ import math
 
 import numpy as np
 
-__all__ = ["SupplyChainOracle", "generate_demand_table", "generate_leadtime_table"]
+__all__ = ["SupplyChainOracle", "generate_demand_table", "generate_leadtime_table", "INFO_KEYS"]
+
+# keys of info['sc_episode']['costs'|'units'] in the reference's order (supplychain_env.py:416-417, :685-686)
+INFO_KEYS = ("stock", "stock_pen", "supply", "process", "process_pen", "ship", "ship_pen", "unmet_dem")
 
 
 # --------------------------------------------------------------------------
@@ -125,6 +128,7 @@ class SupplyChainOracle(object):
         self.by_product = demand_config_by_product
         self.d_range, self.d_std, self.d_peaks = demand_range, demand_std, demand_sen_peaks
         self.d_avg, self.d_norm = avg_demand_range, demand_perturb_norm
+        self.build_info = build_info
         self.rng = np.random.RandomState(seed)
 
         # ---- nodes, in dict insertion order (= act order, :503,544) ----
@@ -239,6 +243,10 @@ class SupplyChainOracle(object):
                             heapq.heappush(nd.q[p], (i + 1, amount))
         self.t = 0
         self.episode_return = 0.0
+        # cumulative statistics of the episode (:684-695); filled only when build_info
+        self.ep_costs = {k: [0] * self.P for k in INFO_KEYS}
+        self.ep_units = {k: [0] * self.P for k in INFO_KEYS}
+        self.ep_rewards = 0
         return self.observation()
 
     # ------------------------------------------------------------------
@@ -260,6 +268,9 @@ class SupplyChainOracle(object):
         """One node, one period (:208-396).  Returns the node's cost."""
         P = self.P
         cost = 0
+        # per-node, per-period statistics (:214-218): every key starts at 0 for every product
+        ec = {k: [0] * P for k in INFO_KEYS}
+        eu = {k: [0] * P for k in INFO_KEYS}
         # 1. arrivals, popped in ascending (time, amount) (:220-228)
         for p in range(P):
             got = 0.0
@@ -271,6 +282,8 @@ class SupplyChainOracle(object):
         for p in range(P):
             if nd.stock[p] > nd.cap[p]:
                 cost += self.c_xstock * (nd.stock[p] - nd.cap[p])
+                ec["stock_pen"][p] = self.c_xstock * (nd.stock[p] - nd.cap[p])
+                eu["stock_pen"][p] = nd.stock[p] - nd.cap[p]
                 nd.stock[p] = nd.cap[p]
         ai = 0   # next action value
         li = 0   # next lead-time value
@@ -284,6 +297,8 @@ class SupplyChainOracle(object):
                         heapq.heappush(nd.q[p], (t + lts[li], amount))
                         li += 1
                     cost += amount * nd.sup_cost[p]
+                    ec["supply"][p] = amount * nd.sup_cost[p]
+                    eu["supply"][p] = amount
         if not nd.last:
             # 4. ship (:262-375)
             D = len(nd.dests)
@@ -316,12 +331,19 @@ class SupplyChainOracle(object):
                     nd.stock[p] -= leaving
                     if nd.proc_cap > 0:
                         cost += leaving * nd.proc_cost[p]                      # :338
+                        ec["process"][p] = leaving * nd.proc_cost[p]
+                        eu["process"][p] = leaving
                     for i in range(D):                                         # :344-348
                         if send[i] > 0:
                             heapq.heappush(nd.dests[i].q[p], (t + lts[base + i], send[i]))
-                    cost += _lsum([send[i] * nd.dest_cost[p][i] for i in range(D)])   # :352-353
+                    ship_cost = _lsum([send[i] * nd.dest_cost[p][i] for i in range(D)])   # :352-353
+                    cost += ship_cost
+                    ec["ship"][p] = ship_cost
+                    eu["ship"][p] = _lsum(send)                                # :356
                 cost += self.c_xproc * over_proc                               # :361
                 cost += self.c_xship * over_ship                               # :366
+                ec["process_pen"][p], eu["process_pen"][p] = self.c_xproc * over_proc, over_proc
+                ec["ship_pen"][p], eu["ship_pen"][p] = self.c_xship * over_ship, over_ship
                 ai += D
         else:
             # 5. retailers serve what they can; the rest is lost (:380-384)
@@ -329,9 +351,18 @@ class SupplyChainOracle(object):
                 served = min(nd.stock[p], demand[p])
                 nd.stock[p] -= served
                 cost += self.c_unmet * (demand[p] - served)
+                ec["unmet_dem"][p] = self.c_unmet * (demand[p] - served)
+                eu["unmet_dem"][p] = demand[p] - served
         # 6. holding (:390-391)
         for p in range(P):
             cost += nd.stock[p] * nd.hold[p]
+            ec["stock"][p] = nd.stock[p] * nd.hold[p]
+            eu["stock"][p] = nd.stock[p]
+        if self.build_info:                                                    # :750-760, node by node
+            for k in INFO_KEYS:
+                for p in range(P):
+                    self.ep_costs[k][p] += ec[k][p]
+                    self.ep_units[k][p] += eu[k][p]
         return cost
 
     def step(self, action):
@@ -359,7 +390,11 @@ class SupplyChainOracle(object):
             total += self._node_step(nd, acts, lts, t, dem)
         reward = -total
         self.episode_return += reward
-        return self.observation(), reward, t == self.T, {}
+        info = {}
+        if self.build_info:
+            self.ep_rewards += reward                                          # :751
+            info = {"sc_episode": {"rewards": self.ep_rewards, "costs": self.ep_costs, "units": self.ep_units}}
+        return self.observation(), reward, t == self.T, info
 
     # ------------------------------------------------------------------
     def _obs_head(self):

@@ -4,13 +4,13 @@ import pytest
 
 from golden_util import beergame_cases, load, sc_cases
 from oracle.beergame_oracle import BeerGameOracle
-from oracle.sc_oracle import SupplyChainOracle
+from oracle.sc_oracle import INFO_KEYS, SupplyChainOracle
 
 
 @pytest.mark.parametrize("name", sc_cases())
 def test_supplychain_oracle_matches_reference_golden(name):
     meta, z = load("sc", name)
-    env = SupplyChainOracle(meta["nodes_info"], **meta["env_kwargs"])
+    env = SupplyChainOracle(meta["nodes_info"], build_info=True, **meta["env_kwargs"])
     assert env.n_actions == meta["A"] and env.n_obs == meta["O"]
     assert (env.n_leadtimes if env.stoch_lt else 0) == meta["K"]
     cap = meta["heap_cap"]
@@ -19,9 +19,14 @@ def test_supplychain_oracle_matches_reference_golden(name):
         obs = env.reset(demand=z["demand"][ep], leadtimes=lts)
         assert np.array_equal(obs, z["obs"][ep, 0])
         for t in range(meta["T"]):
-            obs, r, done, _ = env.step(z["actions"][ep, t])
+            obs, r, done, info = env.step(z["actions"][ep, t])
             assert r == z["reward"][ep, t], (name, ep, t)
             assert done == bool(z["done"][ep, t])
+            epi = info["sc_episode"]                   # build_info statistics (supplychain_env.py:750-760, :793-796)
+            assert epi["rewards"] == z["info_rewards"][ep, t]
+            for ki, key in enumerate(INFO_KEYS):
+                assert [float(x) for x in epi["costs"][key]] == list(z["info_costs"][ep, t, ki]), (name, t, key)
+                assert [float(x) for x in epi["units"][key]] == list(z["info_units"][ep, t, ki]), (name, t, key)
             assert np.array_equal(env.stocks(), z["stock"][ep, t + 1]), (name, ep, t)
             ln, tm, am = env.heap_arrays(cap)
             assert np.array_equal(ln, z["heap_len"][ep, t + 1])

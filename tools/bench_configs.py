@@ -125,7 +125,7 @@ def main():
     rollout_case("beergame-v0 8M envs, fused 35-week episode", "beergame-v0", 8 * M, 35, "fast_f32", it)
     # config 5 (per-GPU share of the 16M-env sweep at 8 GPUs: 1M + 1M), generic kernel for supplychain-v0
     for mode in ("mixed", "fast_f32"):
-        rollout_case("C5 supplychain-v0 demo chain (stochastic lead times), 1M envs, generic kernel", "supplychain-v0", M, 32,
+        rollout_case("C5 supplychain-v0 demo chain (stochastic lead times avg 2 / max 4), 1M envs", "supplychain-v0", M, 32,
                      mode, max(2, it // 3))
     rollout_case("C5 supplychain-v0 demo chain, exact_f64 heapq-exact kernel, 128k envs", "supplychain-v0", 1 << 17, 16,
                  "exact_f64", 2)
