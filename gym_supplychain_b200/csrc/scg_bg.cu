@@ -13,8 +13,12 @@
 
 namespace scg {
 
+// PF = how many weeks ahead the action row of the 4-level fast path is requested (memory-level parallelism:
+// one 16-byte load per lane per week would leave only ~8 KB in flight per SM).
+constexpr int BG_PF = 4;
+
 template <int LMAX, int RMAX, bool STATIC>
-__global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
+__global__ void __launch_bounds__(256, STATIC ? 2 : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
                                                  const int32_t* __restrict__ inj_delays, RngKey key, long long first_env,
                                                  int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
                                                  int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
@@ -23,6 +27,13 @@ __global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const
     const long long n = st.n;
     const int L = STATIC ? LMAX : sp.L;
     const int RING = STATIC ? RMAX : sp.ring;
+    // the per-week demand / delay tables are shared by every env: stage them in shared memory once per block
+    // (a dependent global load per week, even an L1 hit, was the dominant stall of the first version)
+    extern __shared__ int s_tab[];
+    int* s_dem = s_tab;
+    int* s_del = s_tab + sp.T;
+    for (int i = threadIdx.x; i < sp.T; i += blockDim.x) { s_dem[i] = sp.demand[i]; s_del[i] = sp.delays[i]; }
+    __syncthreads();
     ReturnStats rs; rs.init();
     if (env < n) {
         int inv[LMAX], back[LMAX], placed[LMAX], tr[RMAX][LMAX];
@@ -57,17 +68,22 @@ __global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const
             if (obs == nullptr) return;
             if (STATIC && LMAX == 4) {
                 int4 o = make_int4(off + inv[0] - back[0], off + inv[1] - back[1], off + inv[2] - back[2], off + inv[3] - back[3]);
-                reinterpret_cast<int4*>(obs)[io] = o;
+                __stcs(reinterpret_cast<int4*>(obs) + io, o);        // streaming store: written once, never re-read here
             } else {
                 for (int i = 0; i < L; ++i) obs[io * L + i] = off + inv[i] - back[i];
             }
         };
         if (n_steps == 0) write_obs(env);
-        for (int s = 0; s < n_steps; ++s) {
+        constexpr bool kFast4 = STATIC && LMAX == 4;
+        const bool pipelined = kFast4 && actions != nullptr;
+        const int4* act4 = reinterpret_cast<const int4*>(actions);
+
+        // one week of one env; `a_now` is the (pre-loaded) action row of the 4-level fast path
+        auto week_step = [&](int s, int4 a_now) {
             const long long io = (long long)s * n + env;
             if (week >= sp.T) {                                        // finished, not auto-reset: frozen
                 write_obs(io); reward[io] = 0; done[io] = 1;
-                continue;
+                return;
             }
             int act[LMAX];
             if (actions == nullptr) {                                  // random policy, keyed (env, episode, week)
@@ -78,8 +94,7 @@ __global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const
                     if (i < L) act[i] = sp.version == 2 ? uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), 0, (unsigned)sp.max_order)
                                                         : uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), -2, 7);
             } else if (STATIC && LMAX == 4) {
-                const int4 a = reinterpret_cast<const int4*>(actions)[io];
-                act[0] = a.x; act[1] = a.y; act[2] = a.z; act[3] = a.w;
+                act[0] = a_now.x; act[1] = a_now.y; act[2] = a_now.z; act[3] = a_now.w;
             } else {
                 for (int i = 0; i < L; ++i) act[i] = actions[io * L + i];
             }
@@ -92,18 +107,18 @@ __global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const
                 for (int k = 0; k + 1 < RMAX; ++k) if (k + 1 < RING) tr[k][i] = tr[k + 1][i];
                 tr[RING - 1][i] = 0;
             }
-            // customer demand and this week's delay
+            // customer demand and this week's delay; when both are stochastic they share one Philox block
+            // keyed (env, episode, week): word x -> demand, word y -> delay (randint(lo, hi): hi exclusive)
             int dem, delay;
+            const bool rnd_dem = !inj_demand && sp.dem_hi > sp.dem_lo, rnd_del = !inj_delays && sp.del_hi > sp.del_lo;
+            Philox4 wk = Philox4{0, 0, 0, 0};
+            if (rnd_dem || rnd_del) wk = rng_block(key, genv, episode, (unsigned)week, STREAM_BG_DEMAND, 0);
             if (inj_demand) dem = inj_demand[(long long)(week - 1) * n + env];
-            else if (sp.dem_hi > sp.dem_lo)
-                dem = uniform_int(rng_block(key, genv, episode, (unsigned)(week - 1), STREAM_BG_DEMAND, 0).x, sp.dem_lo,
-                                  (unsigned)(sp.dem_hi - sp.dem_lo));                     // randint(lo, hi): hi exclusive
-            else dem = sp.demand[week - 1];
+            else if (rnd_dem) dem = uniform_int(wk.x, sp.dem_lo, (unsigned)(sp.dem_hi - sp.dem_lo));
+            else dem = s_dem[week - 1];
             if (inj_delays) delay = inj_delays[(long long)(week - 1) * n + env];
-            else if (sp.del_hi > sp.del_lo)
-                delay = uniform_int(rng_block(key, genv, episode, (unsigned)week, STREAM_BG_DELAY, 0).x, sp.del_lo,
-                                    (unsigned)(sp.del_hi - sp.del_lo));
-            else delay = sp.delays[week - 1];
+            else if (rnd_del) delay = uniform_int(wk.y, sp.del_lo, (unsigned)(sp.del_hi - sp.del_lo));
+            else delay = s_del[week - 1];
             // 2. fill orders (:79-89)
             int incoming[LMAX], fill[LMAX], deliver[LMAX];
 #pragma unroll
@@ -149,6 +164,31 @@ __global__ void __launch_bounds__(256) bg_kernel(BgDevSpec sp, BgState st, const
             write_obs(io);
             reward[io] = r;
             done[io] = fin ? 1 : 0;
+        };
+
+        if (pipelined) {
+            // groups of BG_PF weeks, double-buffered: the rows of group g+1 are requested before group g is computed
+            // and only copied into `cur` afterwards, so BG_PF independent 16-byte loads per lane stay in flight
+            int4 cur[BG_PF], nxt[BG_PF];
+#pragma unroll
+            for (int u = 0; u < BG_PF; ++u) {
+                cur[u] = make_int4(0, 0, 0, 0);
+                if (u < n_steps) cur[u] = __ldcs(act4 + ((long long)u * n + env));
+            }
+            for (int g = 0; g < n_steps; g += BG_PF) {
+#pragma unroll
+                for (int u = 0; u < BG_PF; ++u) {
+                    nxt[u] = make_int4(0, 0, 0, 0);
+                    if (g + BG_PF + u < n_steps) nxt[u] = __ldcs(act4 + ((long long)(g + BG_PF + u) * n + env));
+                }
+#pragma unroll
+                for (int u = 0; u < BG_PF; ++u)
+                    if (g + u < n_steps) week_step(g + u, cur[u]);
+#pragma unroll
+                for (int u = 0; u < BG_PF; ++u) cur[u] = nxt[u];
+            }
+        } else {
+            for (int s = 0; s < n_steps; ++s) week_step(s, make_int4(0, 0, 0, 0));
         }
         st.week[env] = week; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
 #pragma unroll
@@ -168,8 +208,10 @@ int bg_run(const BgRun& r) {
     const unsigned blocks = (unsigned)((r.st.n + threads - 1) / threads);
     const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
+    const size_t smem = (size_t)2 * r.sp.T * sizeof(int);
+    if (smem > 48 * 1024) { set_error("beer game: more than 6144 weeks per episode not supported"); return SCG_EINVAL; }
 #define SCG_BG_LAUNCH(LM, RM, ST)                                                                              \
-    bg_kernel<LM, RM, ST><<<blocks, threads, 0, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,      \
+    bg_kernel<LM, RM, ST><<<blocks, threads, smem, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,      \
                                                             r.first_env, r.auto_reset, n_steps, r.reset_mask,   \
                                                             do_reset, r.actions, r.obs, r.reward, r.done)
     if (r.sp.L == 4 && r.sp.ring == 2) SCG_BG_LAUNCH(4, 2, true);
