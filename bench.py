@@ -147,6 +147,15 @@ class ClockSampler(object):
                 "reasons": sorted(reasons)}
 
 
+def measured_traffic(mode):
+    """DRAM bytes per launch of the rollout kernel from the committed ncu capture (profiles/r1_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return float(json.load(f)[mode]["bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -312,7 +321,8 @@ def run_ours(args):
                         "api": "scg_rollout_host (pinned host buffers)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "sc_layered_rollout<%s,float,3,3,3,3,2,2>" % ("float" if args.mode == "fast_f32" else "double"), "kernel_ms": kern_ms,
+                             "traffic": measured_traffic(args.mode) if (n_local == 1 << 20 and T == 128) else None,
+                             "traffic_source": "ncu --set full capture of the same command (profiles/r1_traffic.json)", "kernel": "sc_layered_rollout<%s,float,3,3,3,3,2,2>" % ("float" if args.mode == "fast_f32" else "double"), "kernel_ms": kern_ms,
                              "peak_source": peak_src, "bytes_per_launch": n_local * T * BYTES_PER_ENV_STEP},
                 "cpu_baseline": cpu, "alt_modes": alt,
                 "episodes_finished": cnt, "mean_episode_return": mean}

@@ -17,5 +17,6 @@ from .envs import (BeerGameEnv, BeerGameEnv2, SupplyChain2perStageEnv, SupplyCha
                    SupplyChainMultiProduct_IncreasingCosts, SupplyChainNPerStage)
 from .registration import make, register, registered_ids  # noqa: F401
 from .spec import FlatSpec  # noqa: F401
+from .vector import GpuVecEnv  # noqa: F401
 
 __version__ = "0.1.0"

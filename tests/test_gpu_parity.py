@@ -487,3 +487,20 @@ def test_build_info_single_env_dict_and_reset():
     got = torch.stack([info["sc_episode"]["costs"][k][:, 3] for k in ("stock", "stock_pen", "supply", "process",
                                                                        "process_pen", "ship", "ship_pen", "unmet_dem")]).cpu().numpy()
     assert np.allclose(got, z["info_costs"][0, 19], rtol=1e-6, atol=1e-3)
+
+
+def test_gym_vector_adapter_numpy_io_and_episode_infos():
+    venv = gsc.GpuVecEnv("supplychain-2perstage-v0", num_envs=256, numpy_io=True, seed=3, total_time_steps=10)
+    assert venv.num_envs == 256 and venv.single_action_space.shape == (14,) and venv.single_observation_space.shape == (27,)
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (256, 27)
+    rs = np.random.RandomState(0)
+    total = np.zeros(256)
+    for t in range(10):
+        venv.step_async(rs.uniform(-1, 1, (256, 14)).astype(np.float32))
+        obs, rew, dones, infos = venv.step_wait()
+        total += rew
+        assert dones.all() == (t == 9)
+    assert np.allclose(infos["episode"]["r"], total, rtol=1e-6) and len(infos["episode"]["env_index"]) == 256
+    assert np.all(obs[:, -1] == 1.0)                       # auto-reset: first observation of the next episode
+    venv.close()
