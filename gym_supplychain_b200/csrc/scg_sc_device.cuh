@@ -187,9 +187,9 @@ template <class Real>
 struct RingGlobal {
     static constexpr bool kTwoPhase = true;    // all arrivals first, then all node actions
     static constexpr bool kExactObs = false;
-    Real* stock; Real* slot; long long n; int ring;
-    __device__ __forceinline__ RingGlobal(const ScState<Real>& st, long long env, int ring_)
-        : stock(st.stock + env), slot(st.slot + env), n(st.n), ring(ring_) {}
+    Real* stock; Real* slot; long long n; int ring;     // n = element stride (n_envs in HBM, blockDim.x in shared memory)
+    __device__ __forceinline__ RingGlobal(Real* stock_, Real* slot_, long long stride, int ring_)
+        : stock(stock_), slot(slot_), n(stride), ring(ring_) {}
     __device__ __forceinline__ Real get_stock(int np) const { return stock[(long long)np * n]; }
     __device__ __forceinline__ void set_stock(int np, Real v) { stock[(long long)np * n] = v; }
     __device__ __forceinline__ Real slot_at(int np, int k) const { return slot[((long long)np * ring + k) * n]; }
@@ -223,8 +223,8 @@ struct HeapGlobal {
     static constexpr bool kTwoPhase = false;   // reference order: node by node
     static constexpr bool kExactObs = true;
     double* stock; int* hlen; int* htime; double* hamt; long long n; int cap;
-    __device__ __forceinline__ HeapGlobal(const ScState<double>& st, long long env, int cap_)
-        : stock(st.stock + env), hlen(st.hlen + env), htime(st.htime + env), hamt(st.hamt + env), n(st.n), cap(cap_) {}
+    __device__ __forceinline__ HeapGlobal(double* stock_, int* hlen_, int* htime_, double* hamt_, long long stride, int cap_)
+        : stock(stock_), hlen(hlen_), htime(htime_), hamt(hamt_), n(stride), cap(cap_) {}
     __device__ __forceinline__ double get_stock(int np) const { return stock[(long long)np * n]; }
     __device__ __forceinline__ void set_stock(int np, double v) { stock[(long long)np * n] = v; }
     __device__ __forceinline__ int& len(int np) { return hlen[(long long)np * n]; }
@@ -591,20 +591,35 @@ struct GlobalObs {
     __device__ __forceinline__ void put(int idx, Real v) { if (row) row[idx] = (Io)v; }
 };
 
+// contiguous warp copy, 16 B per lane when both sides are 16-byte aligned
+template <class T>
+__device__ __forceinline__ void warp_copy(T* __restrict__ dst, const T* __restrict__ src, int count, int lane) {
+    const bool vec = ((((size_t)dst) | ((size_t)src)) & 15) == 0;
+    constexpr int VW = 16 / (int)sizeof(T);
+    if (vec) {
+        const int nv = count / VW;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+        for (int i = lane; i < nv; i += 32) d4[i] = s4[i];
+        for (int i = nv * VW + lane; i < count; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------
-// Generic kernels: any topology, state in global memory.
+// Generic kernels: any topology (runtime CSR), one thread per env.
+//   use_smem : the env state (stocks + ring, or stocks + heapq arrays) is copied into shared memory for the
+//              whole launch ([element][thread] layout: conflict free) and written back at the end; otherwise
+//              every access goes to HBM (huge specs that do not fit 200 KB per block).
+//   stage_io : each warp moves its 32 action rows / obs rows through a shared-memory tile with coalesced
+//              16-byte accesses instead of 32 strided row accesses per instruction.
 //   MODE 0: FAST ring (Real = float|double);  MODE 1: EXACT heap (Real = double)
 // n_steps = 0 with a mask gives reset(); the same kernel serves step() (n_steps = 1).
 // ---------------------------------------------------------------------------------
 template <class Real, int MODE> struct PipeSel { using type = RingGlobal<Real>; };
 template <> struct PipeSel<double, 1> { using type = HeapGlobal; };
-
-template <class Real, int MODE>
-__device__ __forceinline__ typename PipeSel<Real, MODE>::type make_pipe(const ScState<Real>& st, long long env,
-                                                                        const ScDevSpec<Real>& sp) {
-    if constexpr (MODE == 1) return HeapGlobal(st, env, sp.heapcap);
-    else return RingGlobal<Real>(st, env, sp.ring);
-}
 
 template <class Real, int MODE, class Pp, class Dr, class Ow>
 __device__ __forceinline__ void sc_write_obs(const DynTopoOps<Real>& tp, const ScDevSpec<Real>& sp, Pp& pp, int t, Dr& dr, Ow& ow) {
@@ -616,60 +631,144 @@ template <class Real, class Io, int MODE, bool INFO>
 __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                                                          const unsigned char* __restrict__ reset_mask, int do_reset,
                                                          const Io* __restrict__ actions, Io* __restrict__ obs,
-                                                         Io* __restrict__ reward, unsigned char* __restrict__ done) {
-    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = env < st.n;
+                                                         Io* __restrict__ reward, unsigned char* __restrict__ done,
+                                                         int use_smem, int stage_io) {
+    extern __shared__ __align__(16) unsigned char g_smem[];
+    const int tid = threadIdx.x, bd = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const long long env = (long long)blockIdx.x * bd + tid;
+    const long long n = st.n;
+    const bool active = env < n;
+    const long long env0 = (long long)blockIdx.x * bd + warp * 32;          // first env of this warp
+    const int n_here = env0 >= n ? 0 : (int)((n - env0) < 32 ? (n - env0) : 32);
+    const int NP = sp.N * sp.P;
     ReturnStats rs; rs.init();
+
+    // ---- shared-memory carve-up: [doubles][Reals][ints][per-warp io tiles] ----
+    const int n_amt = (MODE == 1) ? NP * sp.heapcap : 0;                       // heap amounts (double)
+    const int n_real = NP + ((MODE == 1) ? 0 : NP * sp.ring);                  // stocks (+ ring slots)
+    const int n_int = (MODE == 1) ? NP + NP * sp.heapcap : 0;                  // heap lengths + times
+    double* sm_amt = reinterpret_cast<double*>(g_smem);
+    Real* sm_real = reinterpret_cast<Real*>(sm_amt + (use_smem ? (size_t)n_amt * bd : 0));
+    int* sm_int = reinterpret_cast<int*>(sm_real + (use_smem ? (size_t)n_real * bd : 0));
+    size_t io_off = (size_t)(reinterpret_cast<unsigned char*>(sm_int + (use_smem ? (size_t)n_int * bd : 0)) - g_smem);
+    io_off = (io_off + 15) & ~(size_t)15;
+    Io* s_act = reinterpret_cast<Io*>(g_smem + io_off) + (size_t)warp * 32 * (sp.A + sp.O);
+    Io* s_obs = s_act + 32 * sp.A;
+
+    // ---- state pointers of this env: shared memory (stride bd) or HBM (stride n) ----
+    const long long stride = use_smem ? bd : n;
+    Real* p_stock = use_smem ? sm_real + tid : st.stock + env;
+    Real* p_slot = use_smem ? sm_real + (size_t)NP * bd + tid : st.slot + env;
+    double* p_amt = use_smem ? sm_amt + tid : st.hamt + env;
+    int* p_len = use_smem ? sm_int + tid : st.hlen + env;
+    int* p_time = use_smem ? sm_int + (size_t)NP * bd + tid : st.htime + env;
+    if (use_smem && active && !(do_reset && (reset_mask == nullptr || reset_mask[env]))) {
+        for (int i = 0; i < NP; ++i) p_stock[(size_t)i * bd] = st.stock[(long long)i * n + env];
+        if constexpr (MODE == 1) {
+            for (int i = 0; i < NP; ++i) {
+                const int len = st.hlen[(long long)i * n + env];
+                p_len[(size_t)i * bd] = len;
+                for (int k = 0; k < len; ++k) {
+                    p_time[((size_t)i * sp.heapcap + k) * bd] = st.htime[((long long)i * sp.heapcap + k) * n + env];
+                    p_amt[((size_t)i * sp.heapcap + k) * bd] = st.hamt[((long long)i * sp.heapcap + k) * n + env];
+                }
+            }
+        } else {
+            for (int i = 0; i < NP * sp.ring; ++i) p_slot[(size_t)i * bd] = st.slot[(long long)i * n + env];
+        }
+    }
+
+    DynTopoOps<Real> tp(sp);
+    typename PipeSel<Real, MODE>::type pp = [&]() {
+        if constexpr (MODE == 1) return HeapGlobal(p_stock, p_len, p_time, p_amt, stride, sp.heapcap);
+        else return RingGlobal<Real>(p_stock, p_slot, stride, sp.ring);
+    }();
+    int t = 0; unsigned episode = 0; double ep_ret = 0.0;
+    GlobalInfo ginf{(INFO && active) ? st.info + env : nullptr, n, sp.P};
     if (active) {
-        DynTopoOps<Real> tp(sp);
-        auto pp = make_pipe<Real, MODE>(st, env, sp);
-        int t = st.t[env];
-        unsigned episode = (unsigned)st.episode[env];
-        double ep_ret = st.ep_ret[env];
-        GlobalInfo ginf{INFO ? st.info + env : nullptr, st.n, sp.P};
+        t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env];
         if (do_reset && (reset_mask == nullptr || reset_mask[env])) {
             ++episode; t = 0; ep_ret = 0.0;
             pp.reset(tp, sp);
             if constexpr (INFO) ginf.clear();
         }
-        if (n_steps == 0) {       // reset(): emit the current observation
-            DynDemand<Real> dr{sp, in, st.n, env, episode, t};
-            GlobalObs<Real, Io> ow{obs ? obs + env * sp.O : nullptr};
+    }
+    const bool staged_out = stage_io && obs != nullptr;
+    const bool staged_in = stage_io && actions != nullptr;
+
+    if (n_steps == 0 && obs != nullptr) {       // reset(): emit the current observation
+        if (active) {
+            DynDemand<Real> dr{sp, in, n, env, episode, t};
+            GlobalObs<Real, Io> ow{staged_out ? s_obs + lane * sp.O : obs + env * sp.O};
             sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
         }
-        for (int s = 0; s < n_steps; ++s) {
-            const long long io = (long long)s * st.n + env;
-            GlobalObs<Real, Io> ow{obs ? obs + io * sp.O : nullptr};
+        if (staged_out) {
+            __syncwarp();
+            if (n_here > 0) warp_copy<Io>(obs + env0 * sp.O, s_obs, n_here * sp.O, lane);
+        }
+    }
+    for (int s = 0; s < n_steps; ++s) {
+        const long long io = (long long)s * n + env;
+        const long long io0 = (long long)s * n + env0;
+        if (staged_in) {
+            __syncwarp();
+            if (n_here > 0) warp_copy<Io>(s_act, actions + io0 * sp.A, n_here * sp.A, lane);
+            __syncwarp();
+        }
+        if (active) {
+            GlobalObs<Real, Io> ow{obs == nullptr ? nullptr : (staged_out ? s_obs + lane * sp.O : obs + io * sp.O)};
             if (t >= sp.T) {      // finished and not auto-reset: frozen
-                DynDemand<Real> dr{sp, in, st.n, env, episode, t};
+                DynDemand<Real> dr{sp, in, n, env, episode, t};
                 sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
                 reward[io] = (Io)0; done[io] = 1;
-                continue;
-            }
-            ++t;
-            GlobalActions<Real, Io> ar{actions ? actions + io * sp.A : nullptr, actions == nullptr, in.key,
-                                   (unsigned long long)(in.first_env + env), episode, t, Philox4{0, 0, 0, 0}, -1};
-            DynLeadtimes<Real> lr{sp, in, st.n, env, episode, t};
-            DynDemand<Real> dr{sp, in, st.n, env, episode, t};
-            Real cost;
-            if constexpr (INFO) cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr, ginf);
-            else cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr);
-            const Real r = -cost;
-            ep_ret += (double)r;
-            const bool fin = (t == sp.T);
-            if (fin) {
-                rs.add(ep_ret);
-                if (in.auto_reset) {
-                    ++episode; t = 0; ep_ret = 0.0;
-                    pp.reset(tp, sp);
-                    if constexpr (INFO) ginf.clear();
-                    dr.episode = episode; dr.t = 0;
+            } else {
+                ++t;
+                const Io* arow = actions == nullptr ? nullptr : (staged_in ? s_act + lane * sp.A : actions + io * sp.A);
+                GlobalActions<Real, Io> ar{arow, actions == nullptr, in.key, (unsigned long long)(in.first_env + env), episode, t,
+                                           Philox4{0, 0, 0, 0}, -1};
+                DynLeadtimes<Real> lr{sp, in, n, env, episode, t};
+                DynDemand<Real> dr{sp, in, n, env, episode, t};
+                Real cost;
+                if constexpr (INFO) cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr, ginf);
+                else cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dr);
+                const Real r = -cost;
+                ep_ret += (double)r;
+                const bool fin = (t == sp.T);
+                if (fin) {
+                    rs.add(ep_ret);
+                    if (in.auto_reset) {
+                        ++episode; t = 0; ep_ret = 0.0;
+                        pp.reset(tp, sp);
+                        if constexpr (INFO) ginf.clear();
+                        dr.episode = episode; dr.t = 0;
+                    }
                 }
+                sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
+                reward[io] = (Io)r; done[io] = fin ? 1 : 0;
             }
-            sc_write_obs<Real, MODE>(tp, sp, pp, t, dr, ow);
-            reward[io] = (Io)r; done[io] = fin ? 1 : 0;
         }
+        if (staged_out) {
+            __syncwarp();
+            if (n_here > 0) warp_copy<Io>(obs + io0 * sp.O, s_obs, n_here * sp.O, lane);
+        }
+    }
+    if (active) {
         st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
+        if (use_smem) {
+            for (int i = 0; i < NP; ++i) st.stock[(long long)i * n + env] = p_stock[(size_t)i * bd];
+            if constexpr (MODE == 1) {
+                for (int i = 0; i < NP; ++i) {
+                    const int len = p_len[(size_t)i * bd];
+                    st.hlen[(long long)i * n + env] = len;
+                    for (int k = 0; k < len; ++k) {
+                        st.htime[((long long)i * sp.heapcap + k) * n + env] = p_time[((size_t)i * sp.heapcap + k) * bd];
+                        st.hamt[((long long)i * sp.heapcap + k) * n + env] = p_amt[((size_t)i * sp.heapcap + k) * bd];
+                    }
+                }
+            } else {
+                for (int i = 0; i < NP * sp.ring; ++i) st.slot[(long long)i * n + env] = p_slot[(size_t)i * bd];
+            }
+        }
     }
     rs.flush(st.stats);
 }

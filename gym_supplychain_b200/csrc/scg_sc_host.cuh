@@ -174,32 +174,48 @@ static int sc_launch_generic(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((st.n + threads - 1) / threads);
     const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
-    if (r.mode == SCG_MODE_EXACT_F64) {
+    const bool exact = r.mode == SCG_MODE_EXACT_F64;
+    // shared-memory plan: env state per thread + one action/obs tile per warp, within ~200 KB per block
+    const size_t NP = (size_t)sp.N * sp.P;
+    const size_t state_bytes = exact ? NP * sizeof(double) + NP * sizeof(int) + NP * sp.heapcap * (sizeof(double) + sizeof(int))
+                                     : NP * (1 + (size_t)sp.ring) * sizeof(Real);
+    const size_t tile_bytes = (size_t)32 * (sp.A + sp.O) * sizeof(Io);
+    const size_t budget = 200 * 1024;
+    int threads = 128, use_smem = 0, stage_io = 0;
+    for (int th : {128, 64, 32}) {
+        if ((size_t)th * state_bytes + (size_t)(th / 32) * tile_bytes + 64 <= budget) { threads = th; use_smem = 1; stage_io = 1; break; }
+    }
+    if (!use_smem) {
+        for (int th : {128, 64, 32})
+            if ((size_t)th * state_bytes + 64 <= budget) { threads = th; use_smem = 1; break; }
+    }
+    if (!use_smem && (size_t)4 * tile_bytes + 64 <= budget) stage_io = 1;
+    const size_t smem = (use_smem ? (size_t)threads * state_bytes : 0) + (stage_io ? (size_t)(threads / 32) * tile_bytes : 0) + 64;
+    const unsigned blocks = (unsigned)((st.n + threads - 1) / threads);
+#define SCG_GEN_LAUNCH(REAL, IO, MODE_, INFO_)                                                                         \
+    do {                                                                                                               \
+        auto k = sc_generic_kernel<REAL, IO, MODE_, INFO_>;                                                            \
+        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+        k<<<blocks, threads, smem, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset, (const IO*)r.actions,      \
+                                               (IO*)r.obs, (IO*)r.reward, r.done, use_smem, stage_io);                 \
+    } while (0)
+    if (exact) {
         // only the -fmad=false translation unit (Real = Io = double) may instantiate the exact kernel:
         // a second copy compiled with FMA contraction would be an ODR clash and break bit-exactness
         if constexpr (sizeof(Real) == 8 && sizeof(Io) == 8) {
-            if (st.info)
-                sc_generic_kernel<double, double, 1, true><<<blocks, threads, 0, r.stream>>>(
-                    sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
-            else
-                sc_generic_kernel<double, double, 1, false><<<blocks, threads, 0, r.stream>>>(
-                    sp, st, in, n_steps, r.reset_mask, do_reset, (const double*)r.actions, (double*)r.obs, (double*)r.reward, r.done);
+            if (st.info) SCG_GEN_LAUNCH(double, double, 1, true);
+            else SCG_GEN_LAUNCH(double, double, 1, false);
         } else {
             set_error("EXACT mode needs the fp64 translation unit");
             return SCG_EINVAL;
         }
     } else {
-        if (st.info)
-            sc_generic_kernel<Real, Io, 0, true><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
-                                                                                     (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
-        else
-            sc_generic_kernel<Real, Io, 0, false><<<blocks, threads, 0, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset,
-                                                                                      (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
+        if (st.info) SCG_GEN_LAUNCH(Real, Io, 0, true);
+        else SCG_GEN_LAUNCH(Real, Io, 0, false);
     }
+#undef SCG_GEN_LAUNCH
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;
 }

@@ -319,23 +319,6 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
 
-// contiguous warp copy, 16 B per lane when both sides are 16-byte aligned
-template <class Real>
-__device__ __forceinline__ void warp_copy(Real* __restrict__ dst, const Real* __restrict__ src, int count, int lane) {
-    const bool vec = ((((size_t)dst) | ((size_t)src)) & 15) == 0;
-    constexpr int VW = 16 / (int)sizeof(Real);
-    if (vec) {
-        const int nv = count / VW;
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 4
-        for (int i = lane; i < nv; i += 32) d4[i] = s4[i];
-        for (int i = nv * VW + lane; i < count; i += 32) dst[i] = src[i];
-    } else {
-        for (int i = lane; i < count; i += 32) dst[i] = src[i];
-    }
-}
-
 // ---------------------------------------------------------------------------------
 // the fused rollout kernel
 // ---------------------------------------------------------------------------------

@@ -130,6 +130,17 @@ class _ScgEnvBase(object):
         a = None if actions is None else self._as_actions(actions, (T, self.num_envs))
         if out is not None:
             obs, rew, done = out
+            # the kernels write T*N*O (T*N) elements of the handle's I/O dtype through raw pointers: a buffer of the
+            # wrong dtype / shape / device would be an out-of-bounds device write, so check before launching
+            for name, x, shape, dt in (("obs", obs, (T, self.num_envs, self.n_obs), self._io_dtype),
+                                       ("reward", rew, (T, self.num_envs), self._io_dtype),
+                                       ("done", done, (T, self.num_envs), torch.uint8)):
+                if x is None and name == "obs":
+                    continue
+                if (not torch.is_tensor(x) or x.dtype != dt or tuple(x.shape) != shape or not x.is_contiguous()
+                        or x.device != torch.device(self.device)):
+                    raise ValueError("rollout(out=...): %s must be a contiguous %s tensor of shape %s on %s"
+                                     % (name, dt, shape, self.device))
         else:
             obs = torch.empty((T, self.num_envs, self.n_obs), dtype=self._io_dtype, device=self.device) if write_obs else None
             rew = torch.empty((T, self.num_envs), dtype=self._io_dtype, device=self.device)

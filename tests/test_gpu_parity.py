@@ -504,3 +504,21 @@ def test_gym_vector_adapter_numpy_io_and_episode_infos():
     assert np.allclose(infos["episode"]["r"], total, rtol=1e-6) and len(infos["episode"]["env_index"]) == 256
     assert np.all(obs[:, -1] == 1.0)                       # auto-reset: first observation of the next episode
     venv.close()
+
+
+def test_rollout_rejects_output_buffers_of_the_wrong_dtype_shape_or_device():
+    """`rollout(out=...)` hands raw pointers to the kernels: a float32 buffer on a float64 handle would be written
+    past its end (this crashed tools/bench_configs.py once), so the host layer must refuse it."""
+    n, T = 70, 5
+    env = gsc.make("supplychain-ntom-v0", num_envs=n, mode="exact_f64", auto_reset=True)
+    env.reset()
+    good = (torch.empty(T, n, env.n_obs, dtype=torch.float64, device="cuda"), torch.empty(T, n, dtype=torch.float64, device="cuda"),
+            torch.empty(T, n, dtype=torch.uint8, device="cuda"))
+    env.rollout(T, out=good)
+    env.rollout(T, out=(None, good[1], good[2]))                      # obs may be skipped
+    bad = [(good[0].float(), good[1], good[2]), (good[0], good[1].float(), good[2]), (good[0], good[1], good[2].bool()),
+           (good[0][:, :-1], good[1], good[2]), (good[0], good[1][:-1], good[2]), (good[0].cpu(), good[1], good[2]),
+           (good[0].transpose(0, 1).contiguous().transpose(0, 1), good[1], good[2])]
+    for out in bad:
+        with pytest.raises(ValueError):
+            env.rollout(T, out=out)

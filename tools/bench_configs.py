@@ -49,8 +49,8 @@ def rollout_case(case, env_id, n, T, mode, iters, in_kernel_actions=False, **kw)
     env = gsc.make(env_id, num_envs=n, seed=0, auto_reset=True, **kw)
     env.reset()
     A, O = env.n_actions, env.n_obs
-    es = 4
-    dt = torch.int32 if "beergame" in env_id else torch.float32
+    dt = torch.int32 if "beergame" in env_id else env._io_dtype      # exact_f64 / fast_f64 handles move float64
+    es = 8 if dt == torch.float64 else 4
     acts = None
     if not in_kernel_actions:
         if dt == torch.int32:
@@ -129,6 +129,14 @@ def main():
                      mode, max(2, it // 3))
     rollout_case("C5 supplychain-v0 demo chain, exact_f64 heapq-exact kernel, 128k envs", "supplychain-v0", 1 << 17, 16,
                  "exact_f64", 2)
+    # runtime-topology (generic) kernels: what an arbitrary nodes_info gets
+    rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "fast_f32", 3, force_generic=True)
+    rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "mixed", 3, force_generic=True)
+    rollout_case("generic kernel: ntom exact_f64 heapq-exact, 128k envs", "supplychain-ntom-v0", 1 << 17, 16, "exact_f64", 2)
+    rollout_case("generic kernel: n-to-m 5-4-7-10 (26 nodes, A=246, O=177), 128k envs", "sc-Nperstage-multiproduct-v0", 1 << 17, 16,
+                 "fast_f32", 2, nodes_per_echelon=[5, 4, 7, 10])
+    rollout_case("generic kernel: 10-per-stage (40 nodes, A=620), 64k envs", "sc-Nperstage-multiproduct-v0", 1 << 16, 8,
+                 "fast_f32", 2, nodes_per_echelon=10)
 
 
 if __name__ == "__main__":
