@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscg.so")
+LIB_PATH = os.environ.get("SCG_LIB") or os.path.join(HERE, "libscg.so")     # SCG_LIB: an experiment build (build.py --tag)
 
 MODE_FAST_F32, MODE_FAST_F64, MODE_EXACT_F64, MODE_MIXED = 0, 1, 2, 3
 MODES = {"fast_f32": MODE_FAST_F32, "fast_f64": MODE_FAST_F64, "exact_f64": MODE_EXACT_F64, "mixed": MODE_MIXED}

@@ -43,8 +43,13 @@ def _deps_mtime():
     return max(newest, os.path.getmtime(os.path.abspath(__file__)))
 
 
-def build(force=False, verbose=False):
-    """Compile every translation unit (in parallel) and link libscg.so.  Returns the library path."""
+def build(force=False, verbose=False, defines=(), tag=None):
+    """Compile every translation unit (in parallel) and link libscg.so.  Returns the library path.
+    `defines` + `tag` build an experiment variant (extra -D flags) as libscg_<tag>.so next to the product library;
+    load it with SCG_LIB=<path> (kernel A/B measurements, never the default)."""
+    global BUILD, LIB
+    if tag:
+        BUILD, LIB = os.path.join(HERE, "_build_" + tag), os.path.join(HERE, "libscg_%s.so" % tag)
     os.makedirs(BUILD, exist_ok=True)
     newest = _deps_mtime()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
@@ -56,7 +61,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(BUILD, src[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
             return obj
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + ARCH + COMMON + list(defines) + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose:
@@ -75,5 +80,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), None)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=[a for a in sys.argv if a.startswith("-D")], tag=tag)
     print(path)

@@ -24,6 +24,13 @@
 
 namespace scg {
 
+#ifndef SCG_TRIM
+#define SCG_TRIM 1              // compile-time kernels: clips written as max(x, 0) arithmetic (fewer fp64 selects)
+#endif
+#ifndef SCG_BRANCHLESS
+#define SCG_BRANCHLESS 0        // compile-time kernels: capacity clips as selects instead of branches
+#endif
+
 constexpr int SC_MAXD = 32;     // max destinations per node in the generic kernels
 constexpr int SC_MAXP = 8;      // max products
 
@@ -132,6 +139,15 @@ template <class Real> __device__ __forceinline__ Real denorm_action(Real a);
 // (a+1)/2 (:697-698).  fma(a, .5, .5) rounds (a+1)/2 once; halving is exact, so it equals fl(a+1)/2 bit for bit.
 template <> __device__ __forceinline__ double denorm_action<double>(double a) { return fma(a, 0.5, 0.5); }
 template <> __device__ __forceinline__ float denorm_action<float>(float a) { return fmaf(a, 0.5f, 0.5f); }
+
+// max(x, 0).  fp64 has no min/max instruction on sm_100 (a compare plus two selects plus a NaN fix-up on the half-rate
+// FP64 pipe), so the double flavour clears the words of a negative value with three integer operations instead.
+template <class Real> __device__ __forceinline__ Real relu(Real x);
+template <> __device__ __forceinline__ float relu<float>(float x) { return fmaxf(x, 0.0f); }
+template <> __device__ __forceinline__ double relu<double>(double x) {
+    const int hi = __double2hiint(x), keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
 
 template <class Real> __device__ __forceinline__ Real clamp_pm1(Real x) {
     return x < (Real)-1 ? (Real)-1 : (x > (Real)1 ? (Real)1 : x);           // np.clip(.., -1, 1), :700-701
@@ -357,7 +373,13 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
             Real s = pp.get_stock(np);
             if (!Pp::kTwoPhase) s = s + pp.arrive(np, t);
             const Real c = tp.cap(n, p);
-            if (s > c) {
+            if constexpr (Tp::kStatic && SCG_TRIM) {
+                // same update as arithmetic: over = max(s - c, 0) is paid for and discarded
+                const Real over = relu<Real>(s - c);
+                cost += tp.c_xstock() * over;
+                inf.add(INFO_STOCK_PEN, p, tp.c_xstock() * over, over);
+                s -= over;
+            } else if (s > c) {
                 const Real pen = tp.c_xstock() * (s - c);
                 cost += pen;
                 inf.add(INFO_STOCK_PEN, p, pen, s - c);
@@ -405,7 +427,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (Tp::kStatic || s > (Real)0) {
                     // limit = min(stock_capacity, stock) (:61-65) is just the stock: it was clipped to the capacity above
                     Real limit = s;
-                    if (Tp::kStatic) limit = limit > (Real)0 ? limit : (Real)0;
+                    if (Tp::kStatic) limit = SCG_TRIM ? relu<Real>(limit) : (limit > (Real)0 ? limit : (Real)0);
                     Real out[MAXD], send[MAXD];
                     tp.ship_cuts(rv, D, limit, out);
                     const Real r = tp.ratio(n, p);
@@ -414,20 +436,63 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     if (factory) {                                           // :298-310
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                         for (int i = 0; i < D; ++i) {
-                            if (out[i] > (Real)0) {
-                                if (out[i] > proc_left) { over_proc += out[i] - proc_left; out[i] = proc_left; }
-                                proc_left -= out[i];
+                            if constexpr (Tp::kStatic && SCG_TRIM) {
+                                // arithmetic form (proc_left >= 0, so a non-positive amount has no excess and
+                                // consumes nothing): ex = what does not fit; the rest is processed
+                                const Real ex = relu<Real>(out[i] - proc_left);
+                                over_proc += ex;
+                                out[i] -= ex;
+                                proc_left -= relu<Real>(out[i]);
+                            } else if constexpr (Tp::kStatic && SCG_BRANCHLESS) {
+                                // same updates as selects: the straight-line schedule of the unrolled kernel is worth more
+                                // than the skipped instructions (measured)
+                                const bool pos = out[i] > (Real)0;
+                                const bool clip = pos && out[i] > proc_left;
+                                const Real ex = out[i] - proc_left;
+                                over_proc += clip ? ex : (Real)0;
+                                out[i] = clip ? proc_left : out[i];
+                                proc_left -= pos ? out[i] : (Real)0;
+                            } else {
+                                if (out[i] > (Real)0) {
+                                    if (out[i] > proc_left) { over_proc += out[i] - proc_left; out[i] = proc_left; }
+                                    proc_left -= out[i];
+                                }
                             }
                             send[i] = tp.div_ratio(out[i], n, p);
                         }
                     }
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {                            // :312-328 (F4a)
-                        if (send[i] > (Real)0 && send[i] > room[i]) {
-                            over_ship += send[i] - room[i];
-                            send[i] = room[i];
-                            out[i] = factory ? send[i] * r : send[i];
-                            room[i] -= out[i];
+                        if constexpr (Tp::kStatic && SCG_TRIM) {
+                            if (!factory) {
+                                // no processing ratio: the capacity left never goes negative, so the clip is
+                                // ex = max(send - room, 0) and a clipped destination is left with no capacity
+                                const Real ex = relu<Real>(send[i] - room[i]);
+                                over_ship += ex;
+                                send[i] -= ex;
+                                out[i] = send[i];
+                                room[i] = ex > (Real)0 ? (Real)0 : room[i];
+                            } else if (send[i] > (Real)0 && send[i] > room[i]) {
+                                over_ship += send[i] - room[i];
+                                send[i] = room[i];
+                                out[i] = send[i] * r;
+                                room[i] -= out[i];
+                            }
+                        } else if constexpr (Tp::kStatic && SCG_BRANCHLESS) {
+                            const bool clip = send[i] > (Real)0 && send[i] > room[i];
+                            const Real ex = send[i] - room[i];
+                            over_ship += clip ? ex : (Real)0;
+                            send[i] = clip ? room[i] : send[i];
+                            const Real o2 = factory ? send[i] * r : send[i];
+                            out[i] = clip ? o2 : out[i];
+                            room[i] -= clip ? o2 : (Real)0;
+                        } else {
+                            if (send[i] > (Real)0 && send[i] > room[i]) {
+                                over_ship += send[i] - room[i];
+                                send[i] = room[i];
+                                out[i] = factory ? send[i] * r : send[i];
+                                room[i] -= out[i];
+                            }
                         }
                     }
                     Real leaving = (Real)0;
@@ -442,7 +507,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     Real sc = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {
-                        if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
+                        if constexpr (Tp::kStatic && SCG_TRIM) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu<Real>(send[i]));
+                        else if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
                         sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
                     }
                     cost += sc;

@@ -82,6 +82,7 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
 static inline bool sc_is_layered(const ScHostSpec& hs, int S, int F, int W, int R, int P, int L, int ML = 0, bool stoch = false) {
     if (ML == 0) ML = L;
     if (hs.N != S + F + W + R || hs.P != P || (hs.stochL != 0) != stoch || hs.avgL != L || hs.maxL != ML || hs.ring != ML) return false;
+    for (double cap : hs.ecap) if (!(cap >= 0)) return false;       // the kernels rely on non-negative ship capacities
     const int cnt[4] = {S, F, W, R};
     const int base[4] = {0, S, S + F, S + F + W};
     for (int e = 0; e < 4; ++e)

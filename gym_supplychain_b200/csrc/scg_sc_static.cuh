@@ -116,8 +116,62 @@ struct LayeredTopo {
 // action a, so the order predicates and the cap are evaluated on the RAW actions (fp32 compares even when
 // the arithmetic type is fp64) and only the final subtraction and product run in Real.
 // (The fp64-exact mode does not use this: it runs the reference's sequential loop, ship_cuts_dyn.)
+#ifndef SCG_RAWCUTS
+#define SCG_RAWCUTS 1
+#endif
+// Same cuts with the predecessor chosen among the RAW (capped) actions -- fp32 selects when the actions are fp32 --
+// and "no predecessor" encoded as the raw action -1 (whose cut point is 0):
+//     amount_i = (capped_i - capped_pred(i)) * (limit / 2)
+// The difference of two fp32 values is exact in fp64 (up to 2^-53 when their exponents are > 29 apart), so this is
+// at least as accurate as subtracting the two rounded cut points.
+template <class Real, class RawT, int D>
+__device__ __forceinline__ void ship_cuts_static_raw(const RawT* r, Real limit, Real* out) {
+    RawT cpd[D], pr[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) cpd[i] = r[i] < (RawT)1 ? r[i] : (RawT)1;
+    if constexpr (D == 1) {
+        pr[0] = (RawT)-1;
+    } else if constexpr (D == 2) {
+        const bool c01 = r[0] <= r[1];
+        pr[0] = c01 ? (RawT)-1 : cpd[1];
+        pr[1] = c01 ? cpd[0] : (RawT)-1;
+    } else if constexpr (D == 3) {
+        const bool c01 = r[0] <= r[1], c02 = r[0] <= r[2], c12 = r[1] <= r[2];
+        auto prev_of = [&](bool bj, bool bk, bool bjk, RawT wj, RawT wk) {
+            const RawT cand = (bk && (!bj || bjk)) ? wk : wj;
+            return (bj || bk) ? cand : (RawT)-1;
+        };
+        pr[0] = prev_of(!c01, !c02, c12, cpd[1], cpd[2]);
+        pr[1] = prev_of(c01, !c12, c02, cpd[0], cpd[2]);
+        pr[2] = prev_of(c02, c12, c01, cpd[0], cpd[1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            RawT prev = (RawT)-1, rprev = (RawT)0;
+            bool has = false;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (j == i) continue;
+                const bool before = (j < i) ? (r[j] <= r[i]) : (r[j] < r[i]);
+                const bool later = !has || (j > 0 && (rprev <= r[j]));
+                const bool take = before && later;
+                prev = take ? cpd[j] : prev;
+                rprev = take ? r[j] : rprev;
+                has = has || before;
+            }
+            pr[i] = prev;
+        }
+    }
+    const Real half = limit * (Real)0.5;
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = ((Real)cpd[i] - (Real)pr[i]) * half;
+}
+
 template <class Real, class RawT, int D>
 __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real* out) {
+    if constexpr (SCG_RAWCUTS) {
+        ship_cuts_static_raw<Real, RawT, D>(r, limit, out);
+    } else {
     Real w[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -160,6 +214,7 @@ __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real
             }
             out[i] = (w[i] - prev) * limit;
         }
+    }
     }
 }
 
@@ -390,7 +445,11 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
         fetch_next_demand(t);
     }
 
-#pragma unroll 1
+#ifndef SCG_LOOP_UNROLL
+#define SCG_LOOP_UNROLL 1
+#endif
+    constexpr int kLoopUnroll = SCG_LOOP_UNROLL;
+#pragma unroll kLoopUnroll
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
         if (bulk_in) {
