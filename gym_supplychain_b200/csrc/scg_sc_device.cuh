@@ -27,6 +27,9 @@ namespace scg {
 #ifndef SCG_TRIM
 #define SCG_TRIM 1              // compile-time kernels: clips written as max(x, 0) arithmetic (fewer fp64 selects)
 #endif
+#ifndef SCG_LOOSE_RELU
+#define SCG_LOOSE_RELU 1        // one-instruction fp64 max(x, 0) where a tiny positive residue is harmless
+#endif
 #ifndef SCG_BRANCHLESS
 #define SCG_BRANCHLESS 0        // compile-time kernels: capacity clips as selects instead of branches
 #endif
@@ -147,6 +150,21 @@ template <> __device__ __forceinline__ float relu<float>(float x) { return fmaxf
 template <> __device__ __forceinline__ double relu<double>(double x) {
     const int hi = __double2hiint(x), keep = ~(hi >> 31);
     return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
+
+// "Loose" max(x, 0) for amounts that are only ever ADDED to or subtracted from O(1)+ quantities, multiplied, or cast to
+// fp32 -- never compared with 0: ONE instruction for a double.  The sign lives in the high word, and for |x| < 2^1017
+// the high word read as an fp32 has that sign and is never a NaN, so fmaxf(high, 0) clears it exactly when x < 0.
+// The low word is left alone: a negative x becomes a denormal < 5e-315 instead of 0, which vanishes in every sum
+// with a normal number and casts to 0.0f.
+template <class Real> __device__ __forceinline__ Real relu_loose(Real x);
+template <> __device__ __forceinline__ float relu_loose<float>(float x) { return fmaxf(x, 0.0f); }
+template <> __device__ __forceinline__ double relu_loose<double>(double x) {
+#if SCG_LOOSE_RELU
+    return __hiloint2double(__float_as_int(fmaxf(__int_as_float(__double2hiint(x)), 0.0f)), __double2loint(x));
+#else
+    return relu<double>(x);
+#endif
 }
 
 template <class Real> __device__ __forceinline__ Real clamp_pm1(Real x) {
@@ -375,7 +393,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
             const Real c = tp.cap(n, p);
             if constexpr (Tp::kStatic && SCG_TRIM) {
                 // same update as arithmetic: over = max(s - c, 0) is paid for and discarded
-                const Real over = relu<Real>(s - c);
+                const Real over = relu_loose<Real>(s - c);
                 cost += tp.c_xstock() * over;
                 inf.add(INFO_STOCK_PEN, p, tp.c_xstock() * over, over);
                 s -= over;
@@ -396,7 +414,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (tp.has_supply(n, p)) {
                     const Real amount = denorm_action<Real>(ar.get(ai)) * tp.sup_cap(n, p);
                     ++ai;
-                    if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
+                    if constexpr (Tp::kStatic && SCG_TRIM && Lr::kConst) pp.push(n * P + p, t, lr.get(li), relu_loose<Real>(amount));
+                    else if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
                     const Real sup = amount * tp.sup_cost(n, p);
                     cost += sup;
                     inf.add(INFO_SUPPLY, p, sup, amount);
@@ -410,7 +429,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
 #pragma unroll(Tp::kStatic ? MAXD : 1)
             for (int i = 0; i < D; ++i) room[i] = tp.ecap(e0 + i);
             Real proc_left = tp.proc_cap(n);
-            const bool factory = proc_left > (Real)0;
+            bool factory = proc_left > (Real)0;
+            if constexpr (Tp::kStatic) factory = tp.is_factory(n);          // known at compile time (sc_is_layered)
             const int base = li;
 #pragma unroll(Tp::kStatic ? 8 : 1)
             for (int p = 0; p < P; ++p) {
@@ -427,7 +447,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (Tp::kStatic || s > (Real)0) {
                     // limit = min(stock_capacity, stock) (:61-65) is just the stock: it was clipped to the capacity above
                     Real limit = s;
-                    if (Tp::kStatic) limit = SCG_TRIM ? relu<Real>(limit) : (limit > (Real)0 ? limit : (Real)0);
+                    if (Tp::kStatic) limit = SCG_TRIM ? relu_loose<Real>(limit) : (limit > (Real)0 ? limit : (Real)0);
                     Real out[MAXD], send[MAXD];
                     tp.ship_cuts(rv, D, limit, out);
                     const Real r = tp.ratio(n, p);
@@ -439,10 +459,10 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                             if constexpr (Tp::kStatic && SCG_TRIM) {
                                 // arithmetic form (proc_left >= 0, so a non-positive amount has no excess and
                                 // consumes nothing): ex = what does not fit; the rest is processed
-                                const Real ex = relu<Real>(out[i] - proc_left);
+                                const Real ex = relu_loose<Real>(out[i] - proc_left);
                                 over_proc += ex;
                                 out[i] -= ex;
-                                proc_left -= relu<Real>(out[i]);
+                                proc_left -= relu_loose<Real>(out[i]);
                             } else if constexpr (Tp::kStatic && SCG_BRANCHLESS) {
                                 // same updates as selects: the straight-line schedule of the unrolled kernel is worth more
                                 // than the skipped instructions (measured)
@@ -467,11 +487,11 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                             if (!factory) {
                                 // no processing ratio: the capacity left never goes negative, so the clip is
                                 // ex = max(send - room, 0) and a clipped destination is left with no capacity
-                                const Real ex = relu<Real>(send[i] - room[i]);
+                                const Real d = send[i] - room[i], ex = relu_loose<Real>(d);
                                 over_ship += ex;
                                 send[i] -= ex;
                                 out[i] = send[i];
-                                room[i] = ex > (Real)0 ? (Real)0 : room[i];
+                                room[i] = d > (Real)0 ? (Real)0 : room[i];
                             } else if (send[i] > (Real)0 && send[i] > room[i]) {
                                 over_ship += send[i] - room[i];
                                 send[i] = room[i];
@@ -507,7 +527,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     Real sc = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {
-                        if constexpr (Tp::kStatic && SCG_TRIM) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu<Real>(send[i]));
+                        if constexpr (Tp::kStatic && SCG_TRIM) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu_loose<Real>(send[i]));
                         else if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
                         sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
                     }
@@ -640,6 +660,7 @@ struct GlobalActions {                 // actions[(step*n + env)*A + idx]  or Ph
 
 template <class Real>
 struct DynLeadtimes {
+    static constexpr bool kConst = false;
     const ScDevSpec<Real>& sp; const ScInputs& in; long long n, env; unsigned episode; int t;
     __device__ __forceinline__ int get(int k) const { return sc_leadtime(sp, in, n, env, episode, t, k); }
 };

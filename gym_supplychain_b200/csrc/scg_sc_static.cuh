@@ -62,6 +62,7 @@ struct LayeredTopo {
     __device__ __forceinline__ int T() const { return c.T; }
     __device__ __forceinline__ constexpr bool last(int n) const { return ech(n) == 3; }
     __device__ __forceinline__ constexpr bool supplier(int n) const { return ech(n) == 0; }
+    __device__ __forceinline__ constexpr bool is_factory(int n) const { return ech(n) == 1; }   // processing capacity > 0 there only
     __device__ __forceinline__ constexpr int ndest(int n) const { return ech(n) == 3 ? 0 : cnt(ech(n) + 1); }
     __device__ __forceinline__ constexpr int ebeg(int n) const {
         return ech(n) == 0 ? loc(n) * F : (ech(n) == 1 ? S * F + loc(n) * W : S * F + F * W + loc(n) * R);
@@ -308,11 +309,15 @@ struct StaticActions {
     __device__ __forceinline__ Real get(int idx) { return (Real)get_raw(idx); }
 };
 
-template <int L> struct ConstLeadtime { __device__ __forceinline__ constexpr int get(int) const { return L; } };
+template <int L> struct ConstLeadtime {
+    static constexpr bool kConst = true;        // no data-dependent lead-time cursor (F4b) to maintain
+    __device__ __forceinline__ constexpr int get(int) const { return L; }
+};
 
 // K lead times of one period packed 4 bits each (value - 1), so that the data-dependent cursor of
 // SC_Node.act (:252-254, F4b) can index them at run time without touching local memory.
 template <int K> struct PackedLeadtimes {
+    static constexpr bool kConst = false;
     static constexpr int NW = (K + 15) / 16;
     unsigned long long w[NW];
     __device__ __forceinline__ void clear() {
