@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--rollout-T", type=int, default=128)
-    ap.add_argument("--e2e-T", type=int, default=8)
+    ap.add_argument("--e2e-T", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-envs-per-worker", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -3,6 +3,15 @@
 // with the reference to ~1e-7 relative per step (tests state the tolerance).
 #include "scg_sc_host.cuh"
 
+// launch shapes (threads per block, min blocks per SM = register cap) of the small variants: their state is a few
+// registers, so what matters is enough resident warps to hide the per-period TMA round trips
+#ifndef SCG_V1_MINB_F32
+#define SCG_V1_MINB_F32 8
+#endif
+#ifndef SCG_V2_MINB_F32
+#define SCG_V2_MINB_F32 4
+#endif
+
 namespace scg {
 
 // static layered instantiations:  id -> (S, F, W, R, P, L)
@@ -24,8 +33,8 @@ int sc_match_variant_f32(const ScHostSpec& hs) {
 int sc_run_f32(const ScRun& r) {
     if (r.op == SC_OP_ROLLOUT && r.mode == SCG_MODE_FAST_F32) {
         switch (r.variant) {
-            case 1: return sc_launch_layered<float, float, 1, 1, 1, 1, 1, 2, 128, 4>(r);
-            case 2: return sc_launch_layered<float, float, 2, 2, 2, 2, 1, 2, 128, 4>(r);
+            case 1: return sc_launch_layered<float, float, 1, 1, 1, 1, 1, 2, 128, SCG_V1_MINB_F32>(r);
+            case 2: return sc_launch_layered<float, float, 2, 2, 2, 2, 1, 2, 128, SCG_V2_MINB_F32>(r);
             case 3: return sc_launch_layered<float, float, 3, 3, 3, 3, 2, 2, 128, 3>(r);
             case 4: return sc_launch_layered<float, float, 1, 1, 1, 3, 1, 2, 128, 4>(r);
             case 5: return sc_launch_layered<float, float, 2, 2, 2, 2, 2, 2, 128, 3>(r);

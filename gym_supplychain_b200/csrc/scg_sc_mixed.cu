@@ -7,6 +7,13 @@
 // Compiled WITH FMA contraction (bit-exactness is the job of scg_sc_f64.cu).
 #include "scg_sc_host.cuh"
 
+#ifndef SCG_V1_MINB_F64
+#define SCG_V1_MINB_F64 5
+#endif
+#ifndef SCG_V2_MINB_F64
+#define SCG_V2_MINB_F64 4
+#endif
+
 namespace scg {
 
 int sc_match_variant_mixed(const ScHostSpec& hs) {
@@ -22,8 +29,8 @@ int sc_match_variant_mixed(const ScHostSpec& hs) {
 int sc_run_mixed(const ScRun& r) {
     if (r.op == SC_OP_ROLLOUT) {
         switch (r.variant) {
-            case 1: return sc_launch_layered<double, float, 1, 1, 1, 1, 1, 2, 128, 3>(r);
-            case 2: return sc_launch_layered<double, float, 2, 2, 2, 2, 1, 2, 128, 3>(r);
+            case 1: return sc_launch_layered<double, float, 1, 1, 1, 1, 1, 2, 128, SCG_V1_MINB_F64>(r);
+            case 2: return sc_launch_layered<double, float, 2, 2, 2, 2, 1, 2, 128, SCG_V2_MINB_F64>(r);
             case 3: return sc_launch_layered<double, float, 3, 3, 3, 3, 2, 2, 64, 4>(r);
             case 4: return sc_launch_layered<double, float, 1, 1, 1, 3, 1, 2, 128, 3>(r);
             case 5: return sc_launch_layered<double, float, 2, 2, 2, 2, 2, 2, 64, 4>(r);
