@@ -64,6 +64,7 @@ PROTOTYPES = [
     ("scg_abi_version", C.c_int, []),
     ("scg_sc_create", C.c_int, [C.POINTER(ScgSupplyChainSpec), C.POINTER(ScgOptions), C.POINTER(_vp)]),
     ("scg_bg_create", C.c_int, [C.POINTER(ScgBeerGameSpec), C.POINTER(ScgOptions), C.POINTER(_vp)]),
+    ("scg_sc_precompile", C.c_int, [C.POINTER(ScgSupplyChainSpec), C.c_int32, C.c_int32]),
     ("scg_destroy", None, [_vp]),
     ("scg_info", C.c_int, [_vp, C.POINTER(ScgInfo)]),
     ("scg_seed", C.c_int, [_vp, C.c_uint64]),

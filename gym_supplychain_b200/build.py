@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "scg_api.cu": [],
     "scg_bg.cu": [],
+    "scg_jit.cu": [],
     "scg_sc_f32.cu": [],
     "scg_sc_f64.cu": ["-fmad=false"],
     "scg_sc_mixed.cu": [],
@@ -72,7 +73,7 @@ def build(force=False, verbose=False, defines=(), tag=None):
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
         objs = list(pool.map(compile_one, UNITS.items()))
-    cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s" % res.stderr[-4000:])

@@ -42,6 +42,7 @@ struct ScgEnv {
     ScState<float> st32{};
     ScState<double> st64{};
     int variant = 0;
+    ScJit* jit = nullptr;           // run-time instantiated kernels (variant == SC_VARIANT_JIT)
     // beer game
     BgHostSpec bhs;
     BgDevSpec bsp{};
@@ -248,6 +249,10 @@ static int sc_dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask
     r.op = op; r.n_steps = n_steps; r.reset_mask = mask; r.actions = actions; r.obs = obs; r.reward = reward; r.done = done;
     r.stream = stream;
     ++h->launches;
+    if (op == SC_OP_ROLLOUT && h->variant == SC_VARIANT_JIT) {
+        if (sc_jit_run(&h->jit, r) == SCG_OK) return SCG_OK;
+        h->variant = 0; h->info.kernel_variant = 0; r.variant = 0;      // reported once on stderr; the generic kernel takes over
+    }
     if (h->opt.mode == SCG_MODE_MIXED) return sc_run_mixed(r);
     return is_f64(h->opt.mode) ? sc_run_f64(r) : sc_run_f32(r);
 }
@@ -309,6 +314,7 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     h->variant = opt->mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(h->hs)
                : opt->mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(h->hs)
                : opt->mode == SCG_MODE_MIXED ? sc_match_variant_mixed(h->hs) : 0;
+    if (h->variant == 0 && sc_jit_match(h->hs, opt->mode)) h->variant = SC_VARIANT_JIT;
     if (opt->flags & (SCG_FLAG_FORCE_GENERIC | SCG_FLAG_BUILD_INFO)) h->variant = 0;
     ScgInfo& I = h->info;
     I.n_envs = opt->n_envs; I.family = 0; I.mode = opt->mode; I.n_actions = h->hs.A; I.n_obs = h->hs.O;
@@ -320,6 +326,17 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     if (rc != SCG_OK) { scg_destroy(h); return rc; }
     *out = h;
     return SCG_OK;
+}
+
+int scg_sc_precompile(const ScgSupplyChainSpec* spec, int32_t mode, int32_t in_kernel_actions) {
+    if (mode < 0 || mode > 3) { set_error("bad mode %d", mode); return SCG_EINVAL; }
+    ScHostSpec hs;
+    int rc = sc_flatten(spec, hs);
+    if (rc != SCG_OK) return rc;
+    const int v = mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(hs) : mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(hs)
+                : mode == SCG_MODE_MIXED ? sc_match_variant_mixed(hs) : 0;
+    if (v > 0) return SCG_OK;                                   // already in the library
+    return sc_jit_precompile(hs, mode, in_kernel_actions != 0);
 }
 
 int scg_bg_create(const ScgBeerGameSpec* s, const ScgOptions* opt, ScgHandle* out) {
@@ -405,6 +422,7 @@ void scg_destroy(ScgHandle h) {
         if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
+    sc_jit_free(h->jit);
     cudaFree(h->info_buf); cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
     delete h;
 }

@@ -5,8 +5,17 @@
 // drawn from one MT19937 stream (supplychain_env.py:641-672, demands_generator.py:33-89):
 // same distributions, different stream (parity vs the reference is by injection, scg_inject).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (NVRTC, scg_jit.cu): no host headers; the CUDA built-ins are predeclared
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long size_t_rtc_unused;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace scg {
 

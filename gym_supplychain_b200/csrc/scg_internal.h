@@ -72,6 +72,14 @@ size_t sc_devspec_size_f64();
 int sc_build_devspec_f32(const ScHostSpec& hs, void** blob_out, void* devspec_out);
 int sc_build_devspec_f64(const ScHostSpec& hs, void** blob_out, void* devspec_out);
 
+// Run-time instantiation of the layered kernel for shapes without a pre-built one (scg_jit.cu)
+struct ScJit;
+bool sc_jit_match(const ScHostSpec& hs, int mode);      // layered chain + NVRTC and the driver entry points are available
+int sc_jit_run(ScJit** cache, const ScRun& r);          // SCG_OK, or an error after which the caller uses the generic kernel
+void sc_jit_free(ScJit* cache);
+int sc_jit_precompile(const ScHostSpec& hs, int mode, bool random_act);   // NVRTC only, no GPU needed
+constexpr int SC_VARIANT_JIT = 100;
+
 // Beer game
 struct BgHostSpec {
     ScgBeerGameSpec s;

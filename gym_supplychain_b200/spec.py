@@ -147,3 +147,14 @@ class FlatSpec(object):
             setattr(s, name, ptr(getattr(self, name).astype(np.float64), C.c_double))
         self._keep = keep
         return s
+
+    def precompile(self, mode="fast_f32", in_kernel_actions=False):
+        """Make sure a compile-time kernel exists for this chain before the first rollout (needs no GPU): chains without a
+        pre-built instantiation get one compiled with NVRTC into the on-disk cache (scg_sc_precompile).  Returns False
+        when the spec can only run on the runtime-topology kernel (not a layered full-bipartite chain)."""
+        lib = _lib.load()
+        rc = lib.scg_sc_precompile(C.byref(self.c_struct()), _lib.MODES[mode], 1 if in_kernel_actions else 0)
+        if rc == -1:                        # SCG_EINVAL: no compile-time kernel for this spec
+            return False
+        _lib.check(rc)
+        return True

@@ -159,6 +159,7 @@ typedef struct ScgInfo {
     int32_t ring_depth;        /* FAST modes: slots per (node, product)                      */
     int32_t heap_capacity;     /* EXACT mode: entries per (node, product) queue              */
     int32_t kernel_variant;    /* 0 generic runtime-topology kernel, >0 a compile-time one   */
+                               /* (100: instantiated at run time for this chain's shape)     */
     int32_t info_values;       /* 16*P when SCG_FLAG_BUILD_INFO, else 0                      */
     int64_t state_bytes;       /* size of the blob for scg_get_state / scg_set_state         */
 } ScgInfo;
@@ -168,6 +169,11 @@ SCG_API int  scg_abi_version(void);
 
 SCG_API int  scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHandle* out);
 SCG_API int  scg_bg_create(const ScgBeerGameSpec* spec, const ScgOptions* opt, ScgHandle* out);
+/* Chains without a pre-built compile-time kernel (ScgInfo.kernel_variant == 100): the kernel template is instantiated
+ * for the chain's shape with NVRTC at the first rollout (10-20 s, cached under $SCG_JIT_CACHE or <library dir>/_jit;
+ * SCG_JIT=0 disables it).  scg_sc_precompile does that compilation ahead of time; it needs no GPU.  Returns 0 when a
+ * compile-time kernel exists or was compiled, SCG_EINVAL when the spec only runs on the runtime-topology kernel. */
+SCG_API int  scg_sc_precompile(const ScgSupplyChainSpec* spec, int32_t mode, int32_t in_kernel_actions);
 SCG_API void scg_destroy(ScgHandle h);
 SCG_API int  scg_info(ScgHandle h, ScgInfo* out);
 

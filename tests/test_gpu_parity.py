@@ -170,7 +170,11 @@ def test_static_variants_are_selected_for_the_named_ids():
         env = gsc.make(env_id, num_envs=64)
         assert env.scg_info.kernel_variant == variant, env_id
     assert gsc.make("supplychain-v0", num_envs=64).scg_info.kernel_variant == 6     # stochastic lead times avg 2 / max 4
-    assert gsc.make("supplychain-v0", num_envs=64, max_leadtime=3).scg_info.kernel_variant == 0   # no instantiation -> generic
+    # no pre-built instantiation: the kernel template is instantiated at run time for the chain's shape (scg_jit.cu) ...
+    assert gsc.make("supplychain-v0", num_envs=64, max_leadtime=3).scg_info.kernel_variant == 100
+    # ... unless asked not to, or the statistics of build_info are wanted (runtime-topology kernel)
+    assert gsc.make("supplychain-v0", num_envs=64, max_leadtime=3, force_generic=True).scg_info.kernel_variant == 0
+    assert gsc.make("supplychain-v0", num_envs=64, max_leadtime=3, build_info=True).scg_info.kernel_variant == 0
 
 
 @pytest.mark.parametrize("env_id", ["supplychain-linear-v0", "supplychain-2perstage-v0", "supplychain-ntom-v0",
@@ -522,3 +526,29 @@ def test_rollout_rejects_output_buffers_of_the_wrong_dtype_shape_or_device():
     for out in bad:
         with pytest.raises(ValueError):
             env.rollout(T, out=out)
+
+
+@pytest.mark.parametrize("mode", ["fast_f32", "mixed", "fast_f64"])
+def test_runtime_instantiated_kernel_matches_the_runtime_topology_kernel(mode):
+    """A chain shape with no pre-built kernel (2-3-2-4, 3 products, lead time 3): the NVRTC instantiation of the layered
+    template (kernel_variant 100) and the runtime-topology kernel simulate the same Philox demands to the same trajectory,
+    with actions from HBM and with the in-kernel random policy; state blobs are interchangeable."""
+    kw = dict(nodes_per_echelon=[2, 3, 2, 4], num_products=3, avg_leadtime=3, max_leadtime=3, total_time_steps=30)
+    n, T = 777, 45
+    a = gsc.make("supplychain-ntom-v0", num_envs=n, seed=11, auto_reset=True, mode=mode, **kw)
+    b = gsc.make("supplychain-ntom-v0", num_envs=n, seed=11, auto_reset=True, mode=mode, force_generic=True, **kw)
+    assert a.scg_info.kernel_variant == 100 and b.scg_info.kernel_variant == 0
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa, ob)
+    acts = (torch.rand(T, n, a.n_actions, device="cuda", dtype=a._io_dtype) * 2 - 1)
+    o1, r1, d1 = a.rollout(T, acts)
+    assert a.scg_info.kernel_variant == 100, "the run-time instantiation failed and fell back"
+    o2, r2, d2 = b.rollout(T, acts)
+    tol = dict(fast_f32=(2e-5, 2e-5), mixed=(1e-6, 5e-7), fast_f64=(1e-11, 1e-11))[mode]
+    assert torch.equal(d1, d2) and int(d1.sum()) == n
+    assert torch.allclose(r1, r2, rtol=tol[0], atol=1e-2 if mode == "fast_f32" else 1e-6)
+    assert torch.allclose(o1, o2, rtol=0, atol=tol[1])
+    o3, r3, d3 = a.rollout(20)                      # in-kernel random policy: same Philox action words in both kernels
+    o4, r4, d4 = b.rollout(20)
+    assert torch.equal(d3, d4)
+    assert torch.allclose(r3, r4, rtol=10 * tol[0], atol=1e-1 if mode == "fast_f32" else 1e-5)

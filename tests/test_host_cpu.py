@@ -157,3 +157,27 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), fn
                 assert "oracle/" not in text and "sc_oracle" not in text and "gym_shim" not in text, fn
+
+
+def test_runtime_instantiation_compiles_without_a_gpu_and_rejects_non_layered_chains(tmp_path, monkeypatch):
+    """scg_sc_precompile: NVRTC instantiates the layered kernel template for a custom chain shape on the CPU box (this also
+    checks the host-side image of the kernel's constant block against sizeof() inside the generated translation unit);
+    a chain that is not full-bipartite between consecutive echelons only has the runtime-topology kernel."""
+    import gym_supplychain_b200 as gsc
+    from gym_supplychain_b200 import FlatSpec, presets
+    monkeypatch.setenv("SCG_JIT_CACHE", str(tmp_path))
+    info, kw = presets.n_per_stage(nodes_per_echelon=[2, 1, 2, 3], num_products=3, avg_leadtime=3, max_leadtime=3)
+    fs = FlatSpec(info, **kw)
+    assert fs.precompile("mixed") is True
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 2 and files[0].endswith(".cubin") and files[1].endswith(".name")
+    assert fs.precompile("mixed") is True and len(list(tmp_path.iterdir())) == 2          # second call: cache hit
+    info2, kw2 = presets.n_per_stage(nodes_per_echelon=2, num_products=1)                   # pre-built (2-2-2-2, P=1)
+    assert FlatSpec(info2, **kw2).precompile("fast_f32") is True and len(list(tmp_path.iterdir())) == 2
+    broken = {k: dict(v) for k, v in info2.items()}
+    first_supplier = next(k for k, v in broken.items() if "supply_capacity" in v)
+    broken[first_supplier]["destinations"] = broken[first_supplier]["destinations"][:1]    # no longer full bipartite
+    broken[first_supplier]["dest_costs"] = [c[:1] if isinstance(c, (list, tuple)) else c for c in broken[first_supplier]["dest_costs"]]
+    broken[first_supplier]["ship_capacity"] = broken[first_supplier]["ship_capacity"][:1]
+    assert FlatSpec(broken, **kw2).precompile("fast_f32") is False
+    assert fs.precompile("exact_f64") is False                                              # heapq-exact mode: runtime-topology kernel only

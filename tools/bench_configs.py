@@ -34,6 +34,9 @@ def timed(fn, iters, warmup=3):
     return a.elapsed_time(b) / iters
 
 
+ONLY = os.environ.get("SCG_BENCH_ONLY", "")
+
+
 def emit(case, n, T, ms, bytes_per_step, **extra):
     v = n * T / (ms * 1e-3)
     gbs = v * bytes_per_step / 1e9
@@ -44,6 +47,8 @@ def emit(case, n, T, ms, bytes_per_step, **extra):
 
 
 def rollout_case(case, env_id, n, T, mode, iters, in_kernel_actions=False, **kw):
+    if ONLY and ONLY not in case:
+        return
     if "beergame" not in env_id:
         kw = dict(kw, mode=mode)
     env = gsc.make(env_id, num_envs=n, seed=0, auto_reset=True, **kw)
@@ -133,6 +138,16 @@ def main():
     rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "fast_f32", 3, force_generic=True)
     rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "mixed", 3, force_generic=True)
     rollout_case("generic kernel: ntom exact_f64 heapq-exact, 128k envs", "supplychain-ntom-v0", 1 << 17, 16, "exact_f64", 2)
+    # chains without a pre-built kernel: the layered template instantiated at run time (kernel_variant 100)
+    for mode in ("fast_f32", "mixed"):
+        rollout_case("run-time instantiated: n-to-m 5-4-7-10 (26 nodes, A=246, O=177), 256k envs", "sc-Nperstage-multiproduct-v0", 1 << 18, 32,
+                     mode, 3, nodes_per_echelon=[5, 4, 7, 10])
+        rollout_case("run-time instantiated: 3-3-3-3, 3 products, stochastic lead times avg 2 / max 4, 512k envs", "supplychain-ntom-v0",
+                     1 << 19, 64, mode, 3, num_products=3, stochastic_leadtimes=True, avg_leadtime=2, max_leadtime=4)
+        rollout_case("run-time instantiated: 2-3-2-4, 1 product, lead time 3, 1M envs", "supplychain-ntom-v0",
+                     1 << 20, 128, mode, 3, nodes_per_echelon=[2, 3, 2, 4], num_products=1, avg_leadtime=3, max_leadtime=3)
+    rollout_case("run-time instantiated: 10-per-stage (40 nodes, A=620, O=..), 64k envs", "sc-Nperstage-multiproduct-v0", 1 << 16, 16,
+                 "fast_f32", 2, nodes_per_echelon=10)
     rollout_case("generic kernel: n-to-m 5-4-7-10 (26 nodes, A=246, O=177), 128k envs", "sc-Nperstage-multiproduct-v0", 1 << 17, 16,
                  "fast_f32", 2, nodes_per_echelon=[5, 4, 7, 10])
     rollout_case("generic kernel: 10-per-stage (40 nodes, A=620), 64k envs", "sc-Nperstage-multiproduct-v0", 1 << 16, 8,
