@@ -15,10 +15,16 @@ namespace scg {
 
 // PF = how many weeks ahead the action row of the 4-level fast path is requested (memory-level parallelism:
 // one 16-byte load per lane per week would leave only ~8 KB in flight per SM).
-constexpr int BG_PF = 4;
+#ifndef SCG_BG_PF
+#define SCG_BG_PF 4
+#endif
+#ifndef SCG_BG_MINB
+#define SCG_BG_MINB 3
+#endif
+constexpr int BG_PF = SCG_BG_PF;
 
 template <int LMAX, int RMAX, bool STATIC>
-__global__ void __launch_bounds__(256, STATIC ? 2 : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
+__global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
                                                  const int32_t* __restrict__ inj_delays, RngKey key, long long first_env,
                                                  int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
                                                  int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
