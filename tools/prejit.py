@@ -18,12 +18,34 @@ def one(job):
     return name, mode, rand, ok, time.time() - t0
 
 
+def extra(job):
+    """Shapes the GPU tests / tools instantiate that are not golden cases."""
+    kw, mode, rand = job
+    from gym_supplychain_b200 import FlatSpec, presets
+    t0 = time.time()
+    if kw == "supplychain-v0/maxL3":
+        from gym_supplychain_b200.envs import SupplyChainMainDemo  # noqa: F401  (its default nodes_info)
+        info, k = presets.main_demo(max_leadtime=3) if hasattr(presets, "main_demo") else (None, None)
+        if info is None:
+            return str(kw), mode, rand, False, 0.0
+    else:
+        info, k = presets.n_per_stage(**kw)
+    ok = FlatSpec(info, **k).precompile(mode, in_kernel_actions=rand)
+    return str(kw), mode, rand, ok, time.time() - t0
+
+
+EXTRA = [dict(nodes_per_echelon=[2, 3, 2, 4], num_products=3, avg_leadtime=3, max_leadtime=3, total_time_steps=30)]
+
+
 def main():
     from golden_util import sc_cases
     jobs = [(n, m, False) for n in sc_cases() for m in ("fast_f32", "mixed", "fast_f64")]
+    xjobs = [(kw, m, r) for kw in EXTRA for m in ("fast_f32", "mixed", "fast_f64") for r in (False, True)]
     with concurrent.futures.ProcessPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:
         for name, mode, rand, ok, dt in ex.map(one, jobs):
             print("%-28s %-9s %s %5.1fs" % (name, mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
+        for name, mode, rand, ok, dt in ex.map(extra, xjobs):
+            print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
 
 
 if __name__ == "__main__":
