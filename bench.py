@@ -92,7 +92,7 @@ def run_reference(args):
                               "which the box does not have); one process per host core"},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -326,12 +326,26 @@ def run_ours(args):
                              "peak_source": peak_src, "bytes_per_launch": n_local * T * BYTES_PER_ENV_STEP},
                 "cpu_baseline": cpu, "alt_modes": alt,
                 "episodes_finished": cnt, "mean_episode_return": mean}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit_line(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner goes to
+    fd 1) has been redirected to stderr by main()."""
+    (_JSON_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_JSON_OUT or sys.stdout).flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                   # fd 1 -> stderr for the rest of the process (and its children)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
