@@ -1,0 +1,106 @@
+"""GPU parity at scale against the plain-C oracle (oracle/sc_oracle.c, itself pinned bit-for-bit on the reference goldens):
+EVERY env of a batch with its own demand table, lead times and actions, whole episodes -- not sampled replays.
+
+  exact_f64 ........ obs / reward / done bit-exact (layered presets AND random non-layered DAGs, stochastic lead times)
+  mixed ............ rewards within 1e-6 relative (north-star bar), canonical obs within 5e-7
+  fast_f32 ......... rewards within 5e-6 relative
+  run-time instantiated kernels (5-4-7-10) held to the same bars."""
+import numpy as np
+import pytest
+import torch
+
+import gym_supplychain_b200 as gsc
+from gym_supplychain_b200 import presets
+from oracle.c_oracle import CSupplyChainOracle
+from test_c_oracle import _random_chain
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(rs, cc, n, T, lo, hi, wide=False):
+    dem = rs.randint(lo, hi + 1, size=(n, T + 1, cc.n_retailers, cc.P)).astype(np.int32)
+    lts = rs.randint(1, 5, size=(n, T, cc.n_leadtimes)).astype(np.int32) if cc.stoch_lt else None
+    a = rs.uniform(-1.2 if wide else -1.0, 1.2 if wide else 1.0, size=(T, n, cc.n_actions)).astype(np.float32)
+    u = rs.uniform(size=a.shape)
+    a[u < 0.04] = 1.0; a[(u >= 0.04) & (u < 0.08)] = -1.0; a[(u >= 0.08) & (u < 0.10)] = 0.0
+    return dem, lts, a
+
+
+def _oracle_run(cc, dem, lts, a, canonical):
+    T, n = a.shape[0], a.shape[1]
+    obs = np.empty((T + 1, n, cc.n_obs)); rew = np.empty((T, n)); done = np.empty((T, n), dtype=bool)
+    for e in range(n):
+        cc.reset(dem[e], None if lts is None else lts[e])
+        obs[0, e] = cc.observation(canonical=canonical)
+        o, r, d = cc.rollout(a[:, e].astype(np.float64), canonical=canonical)
+        obs[1:, e], rew[:, e], done[:, e] = o, r, d.astype(bool)
+    return obs, rew, done
+
+
+def _gpu_run(env, dem, lts, a):
+    env.inject(demand=dem, leadtimes=lts)
+    o0 = env.reset()
+    acts = torch.from_numpy(a).to(device="cuda", dtype=env._io_dtype)
+    o, r, d = env.rollout(a.shape[0], acts)
+    return (np.concatenate([o0.double().cpu().numpy()[None], o.double().cpu().numpy()]), r.double().cpu().numpy(),
+            d.cpu().numpy().astype(bool))
+
+
+def test_exact_f64_whole_batch_bit_exact_vs_c_oracle_ntom_full_episode():
+    info, kw = presets.n_per_stage(nodes_per_echelon=3)
+    cc = CSupplyChainOracle(info, **kw)
+    n, T = 768, 360
+    dem, lts, a = _inputs(np.random.RandomState(5), cc, n, T, 0, 400)
+    ref = _oracle_run(cc, dem, lts, a, canonical=False)
+    env = gsc.make("supplychain-ntom-v0", num_envs=n, mode="exact_f64", auto_reset=False)
+    got = _gpu_run(env, dem, lts, a)
+    assert np.array_equal(got[2], ref[2]) and ref[2][-1].all() and not ref[2][:-1].any()
+    assert np.array_equal(got[1], ref[1])
+    assert np.array_equal(got[0], ref[0])
+
+
+@pytest.mark.parametrize("mode,rtol,oatol", [("mixed", 1e-6, 5e-7), ("fast_f32", 5e-6, 5e-6)])
+@pytest.mark.parametrize("env_id,kw", [("supplychain-ntom-v0", {}), ("supplychain-2perstage-v0", {}),
+                                       ("supplychain-ntom-v0", {"nodes_per_echelon": [5, 4, 7, 10]})])
+def test_fp32_io_modes_whole_batch_vs_c_oracle_full_episode(env_id, kw, mode, rtol, oatol):
+    """Rewards of every env and period within the mode's bar (relative to max(|reference reward|, 1)); canonical obs."""
+    if "2perstage" in env_id:
+        info, okw = presets.two_per_stage()
+        lo, hi = 10, 20
+    else:
+        info, okw = presets.n_per_stage(**kw)
+        lo, hi = 0, 400
+    cc = CSupplyChainOracle(info, **okw)
+    n, T = (96 if kw else 512), 360
+    dem, lts, a = _inputs(np.random.RandomState(6), cc, n, T, lo, hi)
+    ref = _oracle_run(cc, dem, lts, a, canonical=True)
+    env = gsc.make(env_id, num_envs=n, mode=mode, auto_reset=False, **kw)
+    assert env.scg_info.kernel_variant > 0
+    got = _gpu_run(env, dem, lts, a)
+    assert np.array_equal(got[2], ref[2])
+    rel = np.abs(got[1] - ref[1]) / np.maximum(np.abs(ref[1]), 1.0)
+    assert rel.max() <= rtol, (mode, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+    assert np.abs(got[0] - ref[0]).max() <= oatol
+    assert np.allclose(got[1].sum(0), ref[1].sum(0), rtol=1e-6)          # episode returns
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_exact_f64_bit_exact_on_random_non_layered_dags(seed):
+    """Random DAGs (not layered, per-product constants, one processing node, stochastic lead times on half of them,
+    out-of-range actions): the runtime-topology kernel in exact mode reproduces the C oracle bit for bit, every env."""
+    rs = np.random.RandomState(2000 + seed)
+    info, kw = _random_chain(rs)
+    cc = CSupplyChainOracle(info, **kw)
+    n, T = 160, kw["total_time_steps"]
+    dem, lts, a = _inputs(rs, cc, n, T, kw["demand_range"][0], kw["demand_range"][1], wide=True)
+    ref = _oracle_run(cc, dem, lts, a, canonical=False)
+    env = gsc.SupplyChainEnv(info, num_envs=n, mode="exact_f64", auto_reset=False, **kw)
+    assert env.scg_info.kernel_variant == 0
+    got = _gpu_run(env, dem, lts, a)
+    assert np.array_equal(got[2], ref[2])
+    assert np.array_equal(got[1], ref[1]), seed
+    assert np.array_equal(got[0], ref[0]), seed
+    # the fp64 ring kernel on the same DAG: same dynamics up to the summation order inside a slot
+    fast = gsc.SupplyChainEnv(info, num_envs=n, mode="fast_f64", auto_reset=False, **kw)
+    g2 = _gpu_run(fast, dem, lts, a)
+    assert np.allclose(g2[1], ref[1], rtol=1e-12, atol=1e-9)
