@@ -58,6 +58,24 @@ def _cpu_worker(args):
     return done_steps, time.perf_counter() - t0
 
 
+def _cpu_worker_c(args):
+    """The plain-C oracle (oracle/sc_oracle.c) on the same workload: one episode = reset + n_steps periods with obs."""
+    seed, n_envs, n_steps = args
+    import numpy as np
+    from gym_supplychain_b200 import presets
+    from oracle.c_oracle import CSupplyChainOracle
+    info, kw = presets.n_per_stage(nodes_per_echelon=3)
+    env = CSupplyChainOracle(info, **kw)
+    rs = np.random.RandomState(seed)
+    acts = rs.uniform(-1, 1, (n_steps, env.n_actions)).astype(np.float32).astype(np.float64)
+    dem = rs.randint(0, 401, size=(env.T + 1, env.n_retailers, env.P)).astype(np.int32)
+    t0 = time.perf_counter()
+    for _ in range(n_envs):
+        env.reset(dem)
+        env.rollout(acts)
+    return n_envs * n_steps, time.perf_counter() - t0
+
+
 def cpu_sample(pool, cores, envs_per_worker, n_steps, seed0=0):
     t0 = time.perf_counter()
     res = pool.map(_cpu_worker, [(seed0 + i, envs_per_worker, n_steps) for i in range(cores)])
@@ -296,9 +314,22 @@ def run_ours(args):
         with ctx.Pool(cores) as pool:
             cpu_sample(pool, cores, 1, 16)
             n_steps_cpu, wall = cpu_sample(pool, cores, args.cpu_envs_per_worker, T)
-        cpu = {"value": n_steps_cpu / wall, "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": "%d workers x %d envs x %d periods of %s, random policy, incl. reset()" %
-                         (cores, args.cpu_envs_per_worker, T, ENV_ID)}
+            cpu = {"value": n_steps_cpu / wall, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                   "sample": "%d workers x %d envs x %d periods of %s, random policy, incl. reset()" %
+                             (cores, args.cpu_envs_per_worker, T, ENV_ID),
+                   "what": "oracle/sc_oracle.py: the same per-env Python loop as the reference (the reference itself needs `gym`)"}
+            # the plain-C oracle on the same cores, for context (the checker, not the reference's own speed)
+            try:
+                from oracle import c_oracle
+                c_oracle.build()
+                pool.map(_cpu_worker_c, [(i, 2, T) for i in range(cores)])
+                t0 = time.perf_counter()
+                res = pool.map(_cpu_worker_c, [(100 + i, 40 * args.cpu_envs_per_worker, T) for i in range(cores)])
+                wall_c = time.perf_counter() - t0
+                cpu["c_port"] = {"value": sum(r[0] for r in res) / wall_c, "unit": "env-steps/s", "cores": cores,
+                                 "what": "oracle/sc_oracle.c (plain C restatement, gcc -O2), one process per core"}
+            except Exception as e:  # noqa: BLE001
+                cpu["c_port"] = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
