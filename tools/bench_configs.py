@@ -108,6 +108,25 @@ def step_api_case(n, iters):
         del env
 
 
+def big_step_api_case(env_id, n, iters, label):
+    """Policy-in-the-loop use: one launch per period on a large batch (`env.step(actions)`): the state (fp64 in `mixed`) is
+    read and written every period on top of the actions / obs / reward / done."""
+    if ONLY and ONLY not in label:
+        return
+    for mode in ("mixed", "fast_f32"):
+        env = gsc.make(env_id, num_envs=n, mode=mode, seed=0, auto_reset=True)
+        env.reset()
+        A, O = env.n_actions, env.n_obs
+        acts = torch.empty((n, A), device="cuda").uniform_(-1, 1)
+        ms = timed(lambda: env.step(acts), iters)
+        B = 4 * A + 4 * O + 5
+        S = 2 * env.scg_info.state_bytes / n
+        emit(label, n, 1, ms, B, mode=mode, state_bytes_per_env_step=S, achieved_GBps_incl_state=n * (B + S) / (ms * 1e-3) / 1e9,
+             frac_incl_state=n * (B + S) / (ms * 1e-3) / 1e9 / PEAK, kernel_variant=env.scg_info.kernel_variant)
+        del env
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -134,6 +153,8 @@ def main():
                      mode, max(2, it // 3))
     rollout_case("C5 supplychain-v0 demo chain, exact_f64 heapq-exact kernel, 128k envs", "supplychain-v0", 1 << 17, 16,
                  "exact_f64", 2)
+    big_step_api_case("supplychain-ntom-v0", 1 << 20, it * 4, "C4 ntom 1M envs, step() API (one launch per period, state in HBM)")
+    big_step_api_case("supplychain-2perstage-v0", 1 << 20, it * 4, "C3 2perstage 1M envs, step() API (one launch per period, state in HBM)")
     # runtime-topology (generic) kernels: what an arbitrary nodes_info gets
     rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "fast_f32", 3, force_generic=True)
     rollout_case("generic kernel: ntom 256k envs (force_generic)", "supplychain-ntom-v0", 1 << 18, 32, "mixed", 3, force_generic=True)
@@ -148,10 +169,10 @@ def main():
                      1 << 20, 128, mode, 3, nodes_per_echelon=[2, 3, 2, 4], num_products=1, avg_leadtime=3, max_leadtime=3)
     rollout_case("run-time instantiated: 10-per-stage (40 nodes, A=620, O=..), 64k envs", "sc-Nperstage-multiproduct-v0", 1 << 16, 16,
                  "fast_f32", 2, nodes_per_echelon=10)
-    rollout_case("generic kernel: n-to-m 5-4-7-10 (26 nodes, A=246, O=177), 128k envs", "sc-Nperstage-multiproduct-v0", 1 << 17, 16,
-                 "fast_f32", 2, nodes_per_echelon=[5, 4, 7, 10])
-    rollout_case("generic kernel: 10-per-stage (40 nodes, A=620), 64k envs", "sc-Nperstage-multiproduct-v0", 1 << 16, 8,
-                 "fast_f32", 2, nodes_per_echelon=10)
+    rollout_case("generic kernel: n-to-m 5-4-7-10 (26 nodes, A=246, O=177), 128k envs (force_generic)", "sc-Nperstage-multiproduct-v0",
+                 1 << 17, 16, "fast_f32", 2, nodes_per_echelon=[5, 4, 7, 10], force_generic=True)
+    rollout_case("generic kernel: 10-per-stage (40 nodes, A=620), 64k envs (force_generic)", "sc-Nperstage-multiproduct-v0", 1 << 16, 8,
+                 "fast_f32", 2, nodes_per_echelon=10, force_generic=True)
 
 
 if __name__ == "__main__":
