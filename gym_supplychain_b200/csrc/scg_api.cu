@@ -59,6 +59,8 @@ struct ScgEnv {
     // staging for *_host calls
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    void* bounce = nullptr;         // pinned host buffer of the small-batch scg_step_host path
+    size_t bounce_bytes = 0;
     cudaStream_t hstream = nullptr;                 // kernels of the *_host calls
     cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams (PCIe is full duplex)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -423,6 +425,7 @@ void scg_destroy(ScgHandle h) {
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
     sc_jit_free(h->jit);
+    if (h->bounce) cudaFreeHost(h->bounce);
     cudaFree(h->info_buf); cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
     delete h;
 }
@@ -563,8 +566,37 @@ int scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, voi
 }
 
 int scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uint8_t* done) {
-    if (!actions) { set_error("step_host: actions are required"); return SCG_EINVAL; }
-    return scg_rollout_host(h, 1, actions, obs, reward, done);
+    if (check_handle(h) != SCG_OK) return SCG_EINVAL;
+    if (!actions || !reward || !done) { set_error("step_host: actions, reward and done are required"); return SCG_EINVAL; }
+    const size_t n = (size_t)h->opt.n_envs, es = (size_t)h->info.elem_size;
+    const size_t A = h->info.n_actions, O = h->info.n_obs;
+    const size_t b_act = align_up(n * A * es, 256), b_obs = align_up(n * O * es, 256), b_rew = align_up(n * es, 256), b_done = align_up(n, 256);
+    const size_t total = b_act + b_obs + b_rew + b_done;
+    if (total > ((size_t)1 << 20)) return scg_rollout_host(h, 1, actions, obs, reward, done);
+    // small batches (the drop-in single env): latency path.  One stream, one pinned bounce buffer, two copies, one
+    // synchronisation: host -> [actions] -> kernel -> [obs | reward | done] -> host.
+    int rc = set_device(h);
+    if (rc != SCG_OK) return rc;
+    rc = ensure_stage(h, 2 * total);
+    if (rc != SCG_OK) return rc;
+    if (h->bounce_bytes < total) {
+        if (h->bounce) cudaFreeHost(h->bounce);
+        h->bounce = nullptr; h->bounce_bytes = 0;
+        SCG_CUDA(cudaMallocHost(&h->bounce, total));
+        h->bounce_bytes = total;
+    }
+    unsigned char* hb = (unsigned char*)h->bounce;
+    unsigned char* d = (unsigned char*)h->stage;
+    memcpy(hb, actions, n * A * es);
+    SCG_CUDA(cudaMemcpyAsync(d, hb, n * A * es, cudaMemcpyHostToDevice, h->hstream));
+    rc = dispatch(h, SC_OP_ROLLOUT, 1, nullptr, d, obs ? d + b_act : nullptr, d + b_act + b_obs, d + b_act + b_obs + b_rew, h->hstream);
+    if (rc != SCG_OK) return rc;
+    SCG_CUDA(cudaMemcpyAsync(hb + b_act, d + b_act, b_obs + b_rew + b_done, cudaMemcpyDeviceToHost, h->hstream));
+    SCG_CUDA(cudaStreamSynchronize(h->hstream));
+    if (obs) memcpy(obs, hb + b_act, n * O * es);
+    memcpy(reward, hb + b_act + b_obs, n * es);
+    memcpy(done, hb + b_act + b_obs + b_rew, n);
+    return SCG_OK;
 }
 
 int scg_get_state(ScgHandle h, void* blob, void* stream) {

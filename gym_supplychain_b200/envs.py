@@ -73,6 +73,14 @@ class _ScgEnvBase(object):
         lay = (C.c_int64 * 8)()
         _lib.check(lib.scg_state_layout(self._h, C.byref(lay)))
         self._layout = list(lay)
+        if self._single:
+            # the drop-in single env talks numpy: preallocated host buffers and the *_host entry points (one call,
+            # one synchronisation per step -- no torch tensors on this path)
+            npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32}[self._io_dtype]
+            self._np_act = np.zeros(self.n_actions, dtype=npdt)
+            self._np_obs = np.zeros(self.n_obs, dtype=npdt)
+            self._np_rew = np.zeros(1, dtype=npdt)
+            self._np_done = np.zeros(1, dtype=np.uint8)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -184,16 +192,28 @@ class _ScgEnvBase(object):
 
     # ---- gym API ----
     def reset(self, mask=None):
-        obs = self._reset_tensors(mask)
-        return self._to_single_obs(obs) if self._single else obs
+        if self._single:
+            _lib.check(self._lib.scg_reset_host(self._h, None, self._np_obs.ctypes.data))
+            return self._np_to_obs()
+        return self._reset_tensors(mask)
 
     def step(self, action):
         if self._single:
-            a = np.asarray(action)
-            obs, rew, done = self._step_tensors(a.reshape(1, -1))
-            return self._to_single_obs(obs), self._to_single_reward(rew), bool(done.item()), self._info()
+            a = np.asarray(action).reshape(-1)
+            if a.size < self.n_actions:
+                raise ValueError("actions must have shape (%d,), got %s" % (self.n_actions, tuple(np.shape(action))))
+            self._np_act[:] = a[:self.n_actions]                 # trailing extras are ignored by the reference (:716)
+            _lib.check(self._lib.scg_step_host(self._h, self._np_act.ctypes.data, self._np_obs.ctypes.data,
+                                               self._np_rew.ctypes.data, self._np_done.ctypes.data))
+            return self._np_to_obs(), self._np_to_reward(), bool(self._np_done[0]), self._info()
         obs, rew, done = self._step_tensors(action)
         return obs, rew, done, self._info()
+
+    def _np_to_obs(self):
+        return self._np_obs.astype(np.float64)                   # a fresh float64 array each call, like the reference
+
+    def _np_to_reward(self):
+        return float(self._np_rew[0])
 
     def _info(self):
         return {}
@@ -253,6 +273,7 @@ class SupplyChainEnv(_ScgEnvBase):
         d = prep(demand, (T + 1, R, P))
         lt = prep(leadtimes, (T, self.flat.n_leadtimes)) if self.flat.stochastic_leadtimes else None
         self._inj = (d, lt)                                     # keep the tensors alive
+        torch.cuda.current_stream(self.device).synchronize()    # the *_host calls run on the handle's own stream
         _lib.check(self._lib.scg_inject(self._h, self._ptr(d), self._ptr(lt)))
 
     def _to_single_obs(self, obs):
@@ -413,6 +434,7 @@ class _BeerGameBase(_ScgEnvBase):
             raise ValueError("injected delay %d exceeds the in-transit ring depth %d of this env"
                              % (int(dl.max()), self.scg_info.ring_depth))
         self._inj = (d, dl)
+        torch.cuda.current_stream(self.device).synchronize()    # the *_host calls run on the handle's own stream
         _lib.check(self._lib.scg_inject(self._h, self._ptr(d), self._ptr(dl)))
 
     def _to_single_obs(self, obs):
@@ -420,6 +442,12 @@ class _BeerGameBase(_ScgEnvBase):
 
     def _to_single_reward(self, rew):
         return int(rew[0].item())
+
+    def _np_to_obs(self):
+        return self._np_obs.astype(np.int64)
+
+    def _np_to_reward(self):
+        return int(self._np_rew[0])
 
 
 class BeerGameEnv(_BeerGameBase):
