@@ -30,9 +30,6 @@ namespace scg {
 #ifndef SCG_LOOSE_RELU
 #define SCG_LOOSE_RELU 1        // one-instruction fp64 max(x, 0) where a tiny positive residue is harmless
 #endif
-#ifndef SCG_BRANCHLESS
-#define SCG_BRANCHLESS 0        // compile-time kernels: capacity clips as selects instead of branches
-#endif
 
 constexpr int SC_MAXD = 32;     // max destinations per node in the generic kernels
 constexpr int SC_MAXP = 8;      // max products
@@ -463,15 +460,6 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 over_proc += ex;
                                 out[i] -= ex;
                                 proc_left -= relu_loose<Real>(out[i]);
-                            } else if constexpr (Tp::kStatic && SCG_BRANCHLESS) {
-                                // same updates as selects: the straight-line schedule of the unrolled kernel is worth more
-                                // than the skipped instructions (measured)
-                                const bool pos = out[i] > (Real)0;
-                                const bool clip = pos && out[i] > proc_left;
-                                const Real ex = out[i] - proc_left;
-                                over_proc += clip ? ex : (Real)0;
-                                out[i] = clip ? proc_left : out[i];
-                                proc_left -= pos ? out[i] : (Real)0;
                             } else {
                                 if (out[i] > (Real)0) {
                                     if (out[i] > proc_left) { over_proc += out[i] - proc_left; out[i] = proc_left; }
@@ -498,14 +486,6 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 out[i] = send[i] * r;
                                 room[i] -= out[i];
                             }
-                        } else if constexpr (Tp::kStatic && SCG_BRANCHLESS) {
-                            const bool clip = send[i] > (Real)0 && send[i] > room[i];
-                            const Real ex = send[i] - room[i];
-                            over_ship += clip ? ex : (Real)0;
-                            send[i] = clip ? room[i] : send[i];
-                            const Real o2 = factory ? send[i] * r : send[i];
-                            out[i] = clip ? o2 : out[i];
-                            room[i] -= clip ? o2 : (Real)0;
                         } else {
                             if (send[i] > (Real)0 && send[i] > room[i]) {
                                 over_ship += send[i] - room[i];

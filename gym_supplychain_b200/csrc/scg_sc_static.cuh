@@ -117,16 +117,13 @@ struct LayeredTopo {
 // action a, so the order predicates and the cap are evaluated on the RAW actions (fp32 compares even when
 // the arithmetic type is fp64) and only the final subtraction and product run in Real.
 // (The fp64-exact mode does not use this: it runs the reference's sequential loop, ship_cuts_dyn.)
-#ifndef SCG_RAWCUTS
-#define SCG_RAWCUTS 1
-#endif
-// Same cuts with the predecessor chosen among the RAW (capped) actions -- fp32 selects when the actions are fp32 --
-// and "no predecessor" encoded as the raw action -1 (whose cut point is 0):
+// The predecessor itself is chosen among the RAW (capped) actions -- fp32 selects when the actions are fp32 -- with
+// "no predecessor" encoded as the raw action -1 (whose cut point is 0):
 //     amount_i = (capped_i - capped_pred(i)) * (limit / 2)
 // The difference of two fp32 values is exact in fp64 (up to 2^-53 when their exponents are > 29 apart), so this is
-// at least as accurate as subtracting the two rounded cut points.
+// at least as accurate as subtracting two rounded cut points.
 template <class Real, class RawT, int D>
-__device__ __forceinline__ void ship_cuts_static_raw(const RawT* r, Real limit, Real* out) {
+__device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real* out) {
     RawT cpd[D], pr[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) cpd[i] = r[i] < (RawT)1 ? r[i] : (RawT)1;
@@ -166,57 +163,6 @@ __device__ __forceinline__ void ship_cuts_static_raw(const RawT* r, Real limit, 
     const Real half = limit * (Real)0.5;
 #pragma unroll
     for (int i = 0; i < D; ++i) out[i] = ((Real)cpd[i] - (Real)pr[i]) * half;
-}
-
-template <class Real, class RawT, int D>
-__device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real* out) {
-    if constexpr (SCG_RAWCUTS) {
-        ship_cuts_static_raw<Real, RawT, D>(r, limit, out);
-    } else {
-    Real w[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        const RawT capped = r[i] < (RawT)1 ? r[i] : (RawT)1;
-        w[i] = denorm_action<Real>((Real)capped);
-    }
-    if constexpr (D == 1) {
-        out[0] = w[0] * limit;
-    } else if constexpr (D == 2) {
-        const bool c01 = r[0] <= r[1];                       // 0 before 1
-        out[0] = (w[0] - (c01 ? (Real)0 : w[1])) * limit;
-        out[1] = (w[1] - (c01 ? w[0] : (Real)0)) * limit;
-    } else if constexpr (D == 3) {
-        const bool c01 = r[0] <= r[1], c02 = r[0] <= r[2], c12 = r[1] <= r[2];
-        // for destination i with the other two j < k:  bj = before(j,i), bk = before(k,i), bjk = before(j,k);
-        // predecessor = k if bk and (not bj or bjk), else j (if bj), else none
-        auto prev_of = [&](bool bj, bool bk, bool bjk, Real wj, Real wk) {
-            const Real cand = (bk && (!bj || bjk)) ? wk : wj;
-            return (bj || bk) ? cand : (Real)0;
-        };
-        out[0] = (w[0] - prev_of(!c01, !c02, c12, w[1], w[2])) * limit;
-        out[1] = (w[1] - prev_of(c01, !c12, c02, w[0], w[2])) * limit;
-        out[2] = (w[2] - prev_of(c02, c12, c01, w[0], w[1])) * limit;
-    } else {
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            Real prev = (Real)0;
-            RawT rprev = (RawT)0;
-            bool has = false;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                if (j == i) continue;
-                const bool before = (j < i) ? (r[j] <= r[i]) : (r[j] < r[i]);
-                // among the predecessors keep the last one in (value, index) order
-                const bool later = !has || (j > 0 && (rprev <= r[j]));     // j ascending: ties go to the larger index
-                const bool take = before && later;
-                prev = take ? w[j] : prev;
-                rprev = take ? r[j] : rprev;
-                has = has || before;
-            }
-            out[i] = (w[i] - prev) * limit;
-        }
-    }
-    }
 }
 
 template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_, int ML_, bool STOCH_>
@@ -450,11 +396,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
         fetch_next_demand(t);
     }
 
-#ifndef SCG_LOOP_UNROLL
-#define SCG_LOOP_UNROLL 1
-#endif
-    constexpr int kLoopUnroll = SCG_LOOP_UNROLL;
-#pragma unroll kLoopUnroll
+#pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
         if (bulk_in) {
