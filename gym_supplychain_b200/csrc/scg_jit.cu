@@ -361,15 +361,16 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
         g_rtc.GetCUBIN(prog, &cubin[0]);
         g_rtc.DestroyProgram(&prog);
         mkdir(cache.c_str(), 0755);                          // best effort: a read-only tree just recompiles next time
-        const std::string tmp = f_cubin + ".tmp" + std::to_string((long long)getpid());
-        std::ofstream fc(tmp, std::ios::binary);
-        if (fc) {
+        // both files appear atomically (several ranks may be compiling the same kernel): write, then rename; the
+        // reader needs both, and the .name is renamed last
+        const std::string sfx = ".tmp" + std::to_string((long long)getpid());
+        std::ofstream fc(f_cubin + sfx, std::ios::binary), fn(f_name + sfx, std::ios::binary);
+        if (fc && fn) {
             fc.write(cubin.data(), (std::streamsize)cubin.size());
-            fc.close();
-            std::ofstream fn(f_name, std::ios::binary);
             fn << lowered;
-            fn.close();
-            rename(tmp.c_str(), f_cubin.c_str());
+            fc.close(); fn.close();
+            rename((f_cubin + sfx).c_str(), f_cubin.c_str());
+            rename((f_name + sfx).c_str(), f_name.c_str());
         }
     }
     return SCG_OK;
