@@ -273,12 +273,28 @@ def run_ours(args):
                                                                   m["clocks"], m["stats"])
 
     # ---- e2e: host buffers through the C ABI (H2D actions, kernel, D2H obs/reward/done inside the timed region) ----
-    Te = args.e2e_T
-    h_act = torch.empty((Te, n_local, A), dtype=torch.float32).pin_memory()
+    # pinned host buffers: 0.6 GB per period per rank at 1M envs; with many ranks on one host keep the total modest and
+    # fall back to fewer periods if the host refuses to pin that much
+    Te = args.e2e_T if world <= 2 else max(2, min(args.e2e_T, 32 // world))
+    while True:
+        try:
+            h_act = torch.empty((Te, n_local, A), dtype=torch.float32).pin_memory()
+            h_obs = torch.empty((Te, n_local, O), dtype=torch.float32).pin_memory()
+            h_rew = torch.empty((Te, n_local), dtype=torch.float32).pin_memory()
+            h_done = torch.empty((Te, n_local), dtype=torch.uint8).pin_memory()
+            break
+        except RuntimeError:
+            if Te <= 1:
+                raise
+            h_act = h_obs = h_rew = h_done = None
+            Te = max(1, Te // 2)
+    if world > 1:                                                   # every rank must run the same number of periods
+        te = torch.tensor([Te], dtype=torch.int64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MIN)
+        if int(te) < Te:
+            Te = int(te)
+            h_act, h_obs, h_rew, h_done = h_act[:Te], h_obs[:Te], h_rew[:Te], h_done[:Te]
     h_act.uniform_(-1.0, 1.0)
-    h_obs = torch.empty((Te, n_local, O), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((Te, n_local), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((Te, n_local), dtype=torch.uint8).pin_memory()
     for _ in range(2):
         env.rollout_host(Te, h_act, h_obs, h_rew, h_done)
     barrier()
