@@ -361,7 +361,7 @@ def run_ours(args):
                            "bytes_per_env_step": BYTES_PER_ENV_STEP, "auto_reset": True,
                            "l2": "inputs+outputs per step are %.1f GB per GPU (> 126 MB L2): no flush needed"
                                  % (n_local * T * BYTES_PER_ENV_STEP / 1e9),
-                           "collective": "all-reduce of 5 episode-return statistics per step (NCCL)" if world > 1 else "none (1 GPU)"},
+                           "collective": "one all-gather of the 5 episode-return statistics (40 B per rank) per step (NCCL), reduced locally" if world > 1 else "none (1 GPU)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n_local * Te * A * 4,
                         "d2h_bytes_per_step": n_local * Te * (O * 4 + 4 + 1), "rollout_T": Te, "steps": args.e2e_steps,

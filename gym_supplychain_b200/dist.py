@@ -2,7 +2,7 @@
 
 One process per GPU (torchrun); rank r simulates the contiguous range of global env indices
 [first_env, first_env + n_local).  Philox streams are keyed by the GLOBAL env index, so a trajectory does
-not depend on how many GPUs the job uses.  The only collective is the all-reduce of the five
+not depend on how many GPUs the job uses.  The only collective is the reduction of the five
 episode-return statistics (count, sum, sumsq, min, max) -- 40 bytes, NCCL over NVLink on GPUs, gloo in
 the CPU tests.
 """
@@ -18,17 +18,19 @@ def shard_range(n_total, rank, world_size):
 
 
 def allreduce_return_stats(stats, group=None):
-    """stats: float64[5] tensor = (count, sum, sumsq, min, max) of one shard.  Returns the job-wide values.
-    SUM on the first three, MIN / MAX on the last two (three tiny collectives; latency-bound)."""
+    """stats: float64[5] tensor = (count, sum, sumsq, min, max) of one shard.  Returns the job-wide values on every
+    rank.  ONE collective: the 40-byte records are all-gathered and reduced locally (SUM on the first three, MIN / MAX
+    on the last two) -- pure latency, so one NCCL call instead of one per reduction operator."""
     import torch
     import torch.distributed as dist
     out = stats.clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(out[0:3], op=dist.ReduceOp.SUM, group=group)
-        mn, mx = out[3:4].clone(), out[4:5].clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-        out[3:4], out[4:5] = mn, mx
+        parts = [torch.empty_like(out) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, out, group=group)
+        allr = torch.stack(parts)                      # [world, 5]
+        out[0:3] = allr[:, 0:3].sum(0)
+        out[3] = allr[:, 3].min()
+        out[4] = allr[:, 4].max()
     return out
 
 
