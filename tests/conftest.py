@@ -13,6 +13,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """The tests exercise the built C-ABI library; build it (nvcc cross-compiles without a GPU) if the tree is fresh.
+    The product itself never builds implicitly: without libscg.so it fails loudly."""
+    from gym_supplychain_b200 import build as _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
