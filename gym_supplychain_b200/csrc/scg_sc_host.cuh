@@ -185,10 +185,14 @@ static int sc_launch_generic(const ScRun& r) {
     const size_t tile_bytes = (size_t)32 * (sp.A + sp.O) * sizeof(Io);
     const size_t budget = 200 * 1024;
     int threads = 128, use_smem = 0, stage_io = 0;
+    // copying the state into shared memory and back only pays when it is reused over several periods: reset() and
+    // the single-period step() touch every element about once and work on HBM directly
+    const bool want_smem = n_steps >= 3;
     for (int th : {128, 64, 32}) {
+        if (!want_smem) break;
         if ((size_t)th * state_bytes + (size_t)(th / 32) * tile_bytes + 64 <= budget) { threads = th; use_smem = 1; stage_io = 1; break; }
     }
-    if (!use_smem) {
+    if (!use_smem && want_smem) {
         for (int th : {128, 64, 32})
             if ((size_t)th * state_bytes + 64 <= budget) { threads = th; use_smem = 1; break; }
     }
