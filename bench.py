@@ -165,6 +165,33 @@ class ClockSampler(object):
                 "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Several ranks stream 90 GB/s each through host memory in the e2e leg: keep each rank's threads (and so its
+    first-touched pinned buffers) on the NUMA node its GPU hangs off.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                     # 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def measured_traffic(mode):
     """DRAM bytes per launch of the rollout kernel from the committed ncu capture (profiles/r1_traffic.json)."""
     try:
@@ -202,6 +229,7 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # pinned e2e buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -275,7 +303,7 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI (H2D actions, kernel, D2H obs/reward/done inside the timed region) ----
     # pinned host buffers: 0.6 GB per period per rank at 1M envs; with many ranks on one host keep the total modest and
     # fall back to fewer periods if the host refuses to pin that much
-    Te = args.e2e_T if world <= 2 else max(2, min(args.e2e_T, 32 // world))
+    Te = args.e2e_T if world <= 2 else max(4, min(args.e2e_T, 64 // world))
     while True:
         try:
             h_act = torch.empty((Te, n_local, A), dtype=torch.float32).pin_memory()
@@ -365,7 +393,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n_local * Te * A * 4,
                         "d2h_bytes_per_step": n_local * Te * (O * 4 + 4 + 1), "rollout_T": Te, "steps": args.e2e_steps,
-                        "api": "scg_rollout_host (pinned host buffers)"},
+                        "api": "scg_rollout_host (pinned host buffers)", "numa_node": numa},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic(args.mode) if (n_local == 1 << 20 and T == 128) else None,
