@@ -313,6 +313,10 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     const std::string dir = lib_dir(), csrc = dir + "/csrc";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-I" + csrc};
     if (mode == SCG_MODE_FAST_F64) opts.push_back("--fmad=false");      // same contract as scg_sc_f64.cu
+    if (const char* extra = getenv("SCG_JIT_DEFINES")) {                // kernel A/B experiments: "-DX=1 -DY=0"
+        std::istringstream is(extra);
+        for (std::string tok; is >> tok;) opts.push_back(tok);
+    }
 
     // cache key: everything that determines the cubin
     unsigned long long h = 1469598103934665603ull;

@@ -25,7 +25,7 @@
 namespace scg {
 
 #ifndef SCG_TRIM
-#define SCG_TRIM 1              // compile-time kernels: clips written as max(x, 0) arithmetic (fewer fp64 selects)
+#define SCG_TRIM 63             // compile-time kernels: clips written as max(x, 0) arithmetic (fewer fp64 selects)
 #endif
 #ifndef SCG_LOOSE_RELU
 #define SCG_LOOSE_RELU 1        // one-instruction fp64 max(x, 0) where a tiny positive residue is harmless
@@ -388,7 +388,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
             Real s = pp.get_stock(np);
             if (!Pp::kTwoPhase) s = s + pp.arrive(np, t);
             const Real c = tp.cap(n, p);
-            if constexpr (Tp::kStatic && SCG_TRIM) {
+            if constexpr (Tp::kStatic && (SCG_TRIM & 1)) {
                 // same update as arithmetic: over = max(s - c, 0) is paid for and discarded
                 const Real over = relu_loose<Real>(s - c);
                 cost += tp.c_xstock() * over;
@@ -411,7 +411,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (tp.has_supply(n, p)) {
                     const Real amount = denorm_action<Real>(ar.get(ai)) * tp.sup_cap(n, p);
                     ++ai;
-                    if constexpr (Tp::kStatic && SCG_TRIM && Lr::kConst) pp.push(n * P + p, t, lr.get(li), relu_loose<Real>(amount));
+                    if constexpr (Tp::kStatic && (SCG_TRIM & 32) && Lr::kConst) pp.push(n * P + p, t, lr.get(li), relu_loose<Real>(amount));
                     else if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
                     const Real sup = amount * tp.sup_cost(n, p);
                     cost += sup;
@@ -444,7 +444,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (Tp::kStatic || s > (Real)0) {
                     // limit = min(stock_capacity, stock) (:61-65) is just the stock: it was clipped to the capacity above
                     Real limit = s;
-                    if (Tp::kStatic) limit = SCG_TRIM ? relu_loose<Real>(limit) : (limit > (Real)0 ? limit : (Real)0);
+                    if (Tp::kStatic) limit = (SCG_TRIM & 2) ? relu_loose<Real>(limit) : (limit > (Real)0 ? limit : (Real)0);
                     Real out[MAXD], send[MAXD];
                     tp.ship_cuts(rv, D, limit, out);
                     const Real r = tp.ratio(n, p);
@@ -453,12 +453,15 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     if (factory) {                                           // :298-310
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                         for (int i = 0; i < D; ++i) {
-                            if constexpr (Tp::kStatic && SCG_TRIM) {
+                            if constexpr (Tp::kStatic && (SCG_TRIM & 4)) {
                                 // arithmetic form (proc_left >= 0, so a non-positive amount has no excess and
-                                // consumes nothing): ex = what does not fit; the rest is processed
-                                const Real ex = relu_loose<Real>(out[i] - proc_left);
+                                // consumes nothing): ex = what does not fit; the rest is processed.  A clipped
+                                // amount must be EXACTLY proc_left (and the budget then exactly 0), not
+                                // out - (out - proc_left): a residue of 1e-13 where the reference has 0 flips
+                                // `send > 0` below, and with a negative ship capacity (F4a) that is a whole clip.
+                                const Real d = out[i] - proc_left, ex = relu_loose<Real>(d);
                                 over_proc += ex;
-                                out[i] -= ex;
+                                out[i] = d > (Real)0 ? proc_left : out[i];
                                 proc_left -= relu_loose<Real>(out[i]);
                             } else {
                                 if (out[i] > (Real)0) {
@@ -471,7 +474,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     }
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {                            // :312-328 (F4a)
-                        if constexpr (Tp::kStatic && SCG_TRIM) {
+                        if constexpr (Tp::kStatic && (SCG_TRIM & 8)) {
                             if (!factory) {
                                 // no processing ratio: the capacity left never goes negative, so the clip is
                                 // ex = max(send - room, 0) and a clipped destination is left with no capacity
@@ -507,7 +510,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     Real sc = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {
-                        if constexpr (Tp::kStatic && SCG_TRIM) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu_loose<Real>(send[i]));
+                        if constexpr (Tp::kStatic && (SCG_TRIM & 16)) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu_loose<Real>(send[i]));
                         else if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
                         sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
                     }

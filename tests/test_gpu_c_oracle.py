@@ -104,3 +104,65 @@ def test_exact_f64_bit_exact_on_random_non_layered_dags(seed):
     fast = gsc.SupplyChainEnv(info, num_envs=n, mode="fast_f64", auto_reset=False, **kw)
     g2 = _gpu_run(fast, dem, lts, a)
     assert np.allclose(g2[1], ref[1], rtol=1e-12, atol=1e-9)
+
+
+def _random_layered_chain(rs, tight_factory_ship=False):
+    """A random layered full-bipartite chain (1-4 nodes per echelon, 1-3 products, lead time 1-3, constant or stochastic)
+    with PER-NODE random constants: the shapes the run-time instantiation has to get right.
+
+    Factories get ship capacities they cannot exceed unless `tight_factory_ship`: a ship clip at a factory leaves a
+    NEGATIVE capacity for the next product (the reference subtracts raw-material units), after which any
+    positive amount -- including a 1e-14 rounding residue of a just-emptied stock -- is "clipped" to that negative
+    capacity and hundreds of units appear.  The reference's own trajectory is then decided by the last bit of its
+    floating-point sums, which only the bit-exact mode can follow."""
+    cnt = [int(rs.randint(1, 5)) for _ in range(4)]
+    P, L = int(rs.randint(1, 4)), int(rs.randint(1, 4))
+    stoch = bool(rs.randint(0, 2))
+    maxL = L + int(rs.randint(1, 3)) if stoch else L
+    info, kw = presets.n_per_stage(nodes_per_echelon=cnt, num_products=P, avg_leadtime=L, max_leadtime=maxL,
+                                   stochastic_leadtimes=stoch, total_time_steps=50, demand_range=(0, int(rs.randint(50, 400))),
+                                   unmet_demand_cost=int(rs.randint(20, 300)), exceeded_stock_capacity_cost=int(rs.randint(2, 20)),
+                                   exceeded_process_capacity_cost=int(rs.randint(2, 20)), exceeded_ship_capacity_cost=int(rs.randint(2, 20)),
+                                   processing_ratio=int(rs.randint(1, 4)))
+    ri = lambda lo, hi, n: [int(x) for x in rs.randint(lo, hi, n)]              # noqa: E731
+    for nd in info.values():
+        nd["stock_capacity"] = ri(400, 3000, P)
+        nd["initial_stock"] = [int(rs.randint(0, c)) for c in nd["stock_capacity"]]
+        nd["stock_cost"] = ri(1, 4, P)
+        if "supply_capacity" in nd:
+            nd["supply_capacity"], nd["supply_cost"] = ri(100, 900, P), ri(1, 9, P)
+            nd["initial_supply"] = [ri(0, 500, L) for _ in range(P)]
+        else:
+            nd["initial_shipments"] = [ri(0, 500, L) for _ in range(P)]
+        if "processing_capacity" in nd:
+            nd["processing_capacity"], nd["processing_cost"] = int(rs.randint(300, 2500)), ri(1, 15, P)
+        if "destinations" in nd:
+            D = len(nd["destinations"])
+            nd["dest_costs"], nd["ship_capacity"] = [ri(1, 6, D) for _ in range(P)], ri(150, 1500, D)
+            if "processing_capacity" in nd and not tight_factory_ship:
+                nd["ship_capacity"] = [c + 2 * max(nd["stock_capacity"]) for c in nd["ship_capacity"]]
+    return info, kw, cnt
+
+
+@pytest.mark.parametrize("seed,tight", [(s, False) for s in range(8)] + [(0, True), (23, False), (27, False)])
+def test_runtime_instantiated_kernels_on_random_layered_chains_vs_c_oracle(seed, tight):
+    """(0, tight) is a regression: product 0 ship-clipped at a factory (negative capacity left), product 1 with the
+    processing budget exactly exhausted -- its amount must be exactly 0, not a residue, or it is clipped as well."""
+    rs = np.random.RandomState(3000 + seed)
+    info, kw, cnt = _random_layered_chain(rs, tight_factory_ship=tight)
+    okw = {k: v for k, v in kw.items() if k not in ("seed", "build_info")}
+    cc = CSupplyChainOracle(info, **okw)
+    n, T = 96, kw["total_time_steps"]
+    dem, lts, a = _inputs(rs, cc, n, T, kw["demand_range"][0], kw["demand_range"][1], wide=(seed % 2 == 1))
+    if lts is not None:
+        lts = rs.randint(1, kw["max_leadtime"] + 1, size=lts.shape).astype(np.int32)
+    ref = _oracle_run(cc, dem, lts, a, canonical=True)
+    for mode, rtol, oatol in (("mixed", 1e-6, 5e-7), ("fast_f64", 1e-11, 1e-11)):
+        env = gsc.SupplyChainEnv(info, num_envs=n, mode=mode, auto_reset=False, **okw)
+        assert env.scg_info.kernel_variant > 0, (cnt, kw["num_products"])          # pre-built or instantiated at run time
+        got = _gpu_run(env, dem, lts, a)
+        assert env.scg_info.kernel_variant > 0, "the run-time instantiation failed and fell back"
+        assert np.array_equal(got[2], ref[2])
+        rel = np.abs(got[1] - ref[1]) / np.maximum(np.abs(ref[1]), 1.0)
+        assert rel.max() <= rtol, (seed, mode, cnt, rel.max())
+        assert np.abs(got[0] - ref[0]).max() <= oatol, (seed, mode)
