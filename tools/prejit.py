@@ -35,6 +35,20 @@ def extra(job):
 
 
 EXTRA = [dict(nodes_per_echelon=[2, 3, 2, 4], num_products=3, avg_leadtime=3, max_leadtime=3, total_time_steps=30)]
+RANDOM_CHAINS = [(s, False) for s in range(8)] + [(0, True), (23, False), (27, False)]     # tests/test_gpu_c_oracle.py
+
+
+def random_chain(job):
+    """The random layered chains of tests/test_gpu_c_oracle.py (same generator, same seeds)."""
+    (seed, tight), mode = job
+    import numpy as np
+    from gym_supplychain_b200 import FlatSpec
+    from test_gpu_c_oracle import _random_layered_chain
+    t0 = time.time()
+    info, kw, cnt = _random_layered_chain(np.random.RandomState(3000 + seed), tight_factory_ship=tight)
+    okw = {k: v for k, v in kw.items() if k not in ("seed", "build_info")}
+    ok = FlatSpec(info, **okw).precompile(mode)
+    return "random chain %d %s" % (seed, cnt), mode, False, ok, time.time() - t0
 
 
 def main():
@@ -44,6 +58,8 @@ def main():
     with concurrent.futures.ProcessPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:
         for name, mode, rand, ok, dt in ex.map(one, jobs):
             print("%-28s %-9s %s %5.1fs" % (name, mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
+        for name, mode, rand, ok, dt in ex.map(random_chain, [(c, m) for c in RANDOM_CHAINS for m in ("mixed", "fast_f64")]):
+            print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
         for name, mode, rand, ok, dt in ex.map(extra, xjobs):
             print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
 
