@@ -115,3 +115,27 @@ def test_c_beergame_oracle_matches_reference_golden(name):
             obs, r, done, _ = env.step(z["actions"][ep, t])
             assert np.array_equal(obs, z["obs"][ep, t + 1]), (name, ep, t)
             assert r == z["reward"][ep, t] and done == bool(z["done"][ep, t])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_c_beergame_oracle_equals_python_oracle_on_random_configs(seed):
+    from oracle.beergame_oracle import BeerGameOracle
+    rs = np.random.RandomState(7000 + seed)
+    version = 0 if seed % 2 == 0 else 2
+    L, T = int(rs.randint(2, 7)), int(rs.randint(8, 45))
+    inv0 = [int(x) for x in rs.randint(0, 20, L)]
+    ship, orders, ic, bc = int(rs.randint(0, 8)), int(rs.randint(0, 8)), int(rs.randint(1, 4)), int(rs.randint(1, 5))
+    ms, pen = int(rs.randint(20, 120)), int(rs.randint(1, 200))
+    py = BeerGameOracle(version=version, levels=L, customer_demand=[4] * T, initial_inventory=inv0, shipment_delays=[2] * T,
+                        initial_shipment=ship, initial_orders=orders, inv_cost=ic, backlog_cost=bc, max_stock=ms,
+                        exceeded_capacity_penalty=pen, weeks=T)
+    cc = CBeerGameOracle(version=version, levels=L, weeks=T, initial_inventory=inv0, initial_shipment=ship, initial_orders=orders,
+                         inv_cost=ic, backlog_cost=bc, max_stock=ms, exceeded_capacity_penalty=pen)
+    for ep in range(3):
+        dem, dl = rs.randint(0, 17, T), rs.randint(0, 5, T)
+        assert np.array_equal(py.reset(demand=dem, delays=dl), cc.reset(dem, dl))
+        for t in range(T):
+            a = rs.randint(-3, 6, L) if version == 0 else rs.randint(0, 30, L)
+            o1, r1, d1, _ = py.step(a)
+            o2, r2, d2, _ = cc.step(a)
+            assert np.array_equal(o1, o2) and r1 == r2 and d1 == d2, (seed, ep, t)

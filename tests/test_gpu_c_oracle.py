@@ -166,3 +166,87 @@ def test_runtime_instantiated_kernels_on_random_layered_chains_vs_c_oracle(seed,
         rel = np.abs(got[1] - ref[1]) / np.maximum(np.abs(ref[1]), 1.0)
         assert rel.max() <= rtol, (seed, mode, cnt, rel.max())
         assert np.abs(got[0] - ref[0]).max() <= oatol, (seed, mode)
+
+
+AOT_SHAPES = [dict(nodes_per_echelon=[1, 1, 1, 1], num_products=1), dict(nodes_per_echelon=[2, 2, 2, 2], num_products=1),
+              dict(nodes_per_echelon=[2, 2, 2, 2], num_products=2), dict(nodes_per_echelon=[3, 3, 3, 3], num_products=2),
+              dict(nodes_per_echelon=[1, 1, 1, 3], num_products=1),
+              dict(nodes_per_echelon=[2, 2, 2, 2], num_products=1, stochastic_leadtimes=True, avg_leadtime=2, max_leadtime=4)]
+
+
+@pytest.mark.parametrize("k", range(len(AOT_SHAPES)))
+@pytest.mark.parametrize("mode,rtol,oatol", [("mixed", 1e-6, 5e-7), ("fast_f32", 5e-5, 5e-6)])
+def test_prebuilt_kernels_with_random_per_node_constants_vs_c_oracle(k, mode, rtol, oatol):
+    """The six pre-built chain shapes with per-node RANDOM constants (capacities, costs, initial pipeline), lead time 2,
+    out-of-range actions on the odd ones: the kernels only specialise on the shape, every constant is a parameter."""
+    rs = np.random.RandomState(4000 + k)
+    shape = AOT_SHAPES[k]
+    info, kw = presets.n_per_stage(total_time_steps=60, demand_range=(0, int(rs.randint(50, 400))),
+                                   unmet_demand_cost=int(rs.randint(20, 300)), processing_ratio=int(rs.randint(1, 4)), **shape)
+    P, L = kw["num_products"], kw["avg_leadtime"]
+    ri = lambda lo, hi, n: [int(x) for x in rs.randint(lo, hi, n)]              # noqa: E731
+    for nd in info.values():
+        nd["stock_capacity"] = ri(400, 3000, P)
+        nd["initial_stock"] = [int(rs.randint(0, c)) for c in nd["stock_capacity"]]
+        nd["stock_cost"] = ri(1, 4, P)
+        if "supply_capacity" in nd:
+            nd["supply_capacity"], nd["supply_cost"], nd["initial_supply"] = ri(100, 900, P), ri(1, 9, P), [ri(0, 500, L) for _ in range(P)]
+        else:
+            nd["initial_shipments"] = [ri(0, 500, L) for _ in range(P)]
+        if "destinations" in nd:
+            D = len(nd["destinations"])
+            nd["dest_costs"], nd["ship_capacity"] = [ri(1, 6, D) for _ in range(P)], ri(150, 1500, D)
+        if "processing_capacity" in nd:          # factories: tight processing, ship capacity they cannot exceed (see above)
+            nd["processing_capacity"], nd["processing_cost"] = int(rs.randint(300, 2500)), ri(1, 15, P)
+            nd["ship_capacity"] = [c + 2 * max(nd["stock_capacity"]) for c in nd["ship_capacity"]]
+    okw = {x: v for x, v in kw.items() if x not in ("seed", "build_info")}
+    cc = CSupplyChainOracle(info, **okw)
+    n, T = 160, kw["total_time_steps"]
+    dem, lts, a = _inputs(rs, cc, n, T, kw["demand_range"][0], kw["demand_range"][1], wide=(k % 2 == 1))
+    ref = _oracle_run(cc, dem, lts, a, canonical=True)
+    env = gsc.SupplyChainEnv(info, num_envs=n, mode=mode, auto_reset=False, **okw)
+    assert 1 <= env.scg_info.kernel_variant <= 6, env.scg_info.kernel_variant
+    got = _gpu_run(env, dem, lts, a)
+    assert np.array_equal(got[2], ref[2])
+    rel = np.abs(got[1] - ref[1]) / np.maximum(np.abs(ref[1]), 1.0)
+    assert rel.max() <= rtol, (k, mode, rel.max())
+    assert np.abs(got[0] - ref[0]).max() <= oatol
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_beergame_random_configs_whole_batch_bit_exact_vs_c_oracle(seed):
+    """Random beer games (2-6 levels, v0 and v2, per-env demand and delay tables 0..4, random costs / inventories):
+    every env, every week, bit for bit against the C oracle."""
+    from oracle.c_oracle import CBeerGameOracle
+    rs = np.random.RandomState(5000 + seed)
+    version = 0 if seed % 2 == 0 else 2
+    L, T, n = int(rs.randint(2, 7)), int(rs.randint(10, 40)), 300
+    inv0 = [int(x) for x in rs.randint(0, 20, L)]
+    kw = dict(inv_cost=int(rs.randint(1, 4)), backlog_cost=int(rs.randint(1, 5)))
+    ship, orders = int(rs.randint(0, 8)), int(rs.randint(0, 8))
+    max_delay = int(rs.choice([2, 4]))
+    dem = rs.randint(0, 17, size=(n, T)).astype(np.int32)
+    dl = rs.randint(0, max_delay + 1, size=(n, T)).astype(np.int32)
+    if version == 0:
+        env = gsc.BeerGameEnv({"levels": L, "customer_demand": [4] * T, "shipment_delays": [max_delay] * T, "initial_inventory": inv0,
+                               "initial_shipment_value": ship, "initial_orders_value": orders, **kw}, num_envs=n, auto_reset=False)
+        acts = rs.randint(-3, 6, size=(T, n, L)).astype(np.int32)
+        ora = CBeerGameOracle(version=0, levels=L, weeks=T, initial_inventory=inv0, initial_shipment=ship, initial_orders=orders, **kw)
+    else:
+        ms, pen = int(rs.randint(20, 120)), int(rs.randint(1, 200))
+        env = gsc.BeerGameEnv2(max_stock=ms, weeks=T, levels=L, customer_demand=[4] * T, initial_inventory=inv0,
+                               exceeded_capacity_penalty=pen, shipment_delays=[max_delay] * T, initial_shipment=ship,
+                               initial_orders=orders, num_envs=n, auto_reset=False, **kw)
+        acts = rs.randint(0, 30, size=(T, n, L)).astype(np.int32)
+        ora = CBeerGameOracle(version=2, levels=L, weeks=T, initial_inventory=inv0, initial_shipment=ship, initial_orders=orders,
+                              max_stock=ms, exceeded_capacity_penalty=pen, **kw)
+    env.inject(demand=dem, delays=dl)
+    o0 = env.reset()
+    o, r, d = env.rollout(T, torch.from_numpy(acts).cuda())
+    o0, o, r, d = o0.cpu().numpy(), o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy().astype(bool)
+    for e in range(n):
+        obs = ora.reset(dem[e], dl[e])
+        assert np.array_equal(obs, o0[e])
+        for t in range(T):
+            obs, rew, done, _ = ora.step(acts[t, e])
+            assert np.array_equal(obs, o[t, e]) and rew == r[t, e] and done == d[t, e], (seed, e, t)
