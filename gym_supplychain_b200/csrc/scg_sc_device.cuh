@@ -164,6 +164,9 @@ template <> __device__ __forceinline__ double relu_loose<double>(double x) {
 #endif
 }
 
+// everything relu_loose can leave behind is below this; no real quantity of the simulation is
+template <class Real> __device__ __forceinline__ constexpr Real loose_zero() { return sizeof(Real) == 8 ? (Real)1e-300 : (Real)0; }
+
 template <class Real> __device__ __forceinline__ Real clamp_pm1(Real x) {
     return x < (Real)-1 ? (Real)-1 : (x > (Real)1 ? (Real)1 : x);           // np.clip(.., -1, 1), :700-701
 }
@@ -483,7 +486,11 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 send[i] -= ex;
                                 out[i] = send[i];
                                 room[i] = d > (Real)0 ? (Real)0 : room[i];
-                            } else if (send[i] > (Real)0 && send[i] > room[i]) {
+                            } else if (send[i] > loose_zero<Real>() && send[i] > room[i]) {
+                                // a factory's capacity can be NEGATIVE here (after a clip of an earlier product the
+                                // reference subtracts raw-material units, F4a), so this `send > 0` decides a whole
+                                // clip: the denormals that relu_loose leaves where the reference has exact zeros
+                                // (unpushed negative amounts, emptied stocks) must not count as shipments
                                 over_ship += send[i] - room[i];
                                 send[i] = room[i];
                                 out[i] = send[i] * r;
