@@ -104,6 +104,11 @@ def test_exact_f64_bit_exact_on_random_non_layered_dags(seed):
     fast = gsc.SupplyChainEnv(info, num_envs=n, mode="fast_f64", auto_reset=False, **kw)
     g2 = _gpu_run(fast, dem, lts, a)
     assert np.allclose(g2[1], ref[1], rtol=1e-12, atol=1e-9)
+    # and with fp32 I/O (mixed): the north-star bar on every reward, canonical observation
+    canon = _oracle_run(cc, dem, lts, a, canonical=True)
+    g3 = _gpu_run(gsc.SupplyChainEnv(info, num_envs=n, mode="mixed", auto_reset=False, **kw), dem, lts, a)
+    rel = np.abs(g3[1] - canon[1]) / np.maximum(np.abs(canon[1]), 1.0)
+    assert rel.max() <= 1e-6 and np.abs(g3[0] - canon[0]).max() <= 5e-7 and np.array_equal(g3[2], canon[2])
 
 
 def _random_layered_chain(rs, tight_factory_ship=False):
