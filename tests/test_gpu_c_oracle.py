@@ -255,3 +255,21 @@ def test_beergame_random_configs_whole_batch_bit_exact_vs_c_oracle(seed):
         for t in range(T):
             obs, rew, done, _ = ora.step(acts[t, e])
             assert np.array_equal(obs, o[t, e]) and rew == r[t, e] and done == d[t, e], (seed, e, t)
+
+
+@pytest.mark.parametrize("seed", range(0, 40, 1))
+def test_exact_f64_bit_exact_on_random_layered_chains_with_tight_factories(seed):
+    """exact_f64 follows the reference bit for bit on every random chain, including the ones where a ship clip at a factory
+    leaves a negative capacity and the trajectory hinges on a 1e-14 residue (seeds 23 and 27: the cases no tolerance
+    mode can follow)."""
+    rs = np.random.RandomState(3000 + seed)
+    info, kw, cnt = _random_layered_chain(rs, tight_factory_ship=True)
+    okw = {k: v for k, v in kw.items() if k not in ("seed", "build_info")}
+    cc = CSupplyChainOracle(info, **okw)
+    n, T = 96, kw["total_time_steps"]
+    dem, lts, a = _inputs(rs, cc, n, T, kw["demand_range"][0], kw["demand_range"][1], wide=(seed % 2 == 1))
+    if lts is not None:
+        lts = rs.randint(1, kw["max_leadtime"] + 1, size=lts.shape).astype(np.int32)
+    ref = _oracle_run(cc, dem, lts, a, canonical=False)
+    got = _gpu_run(gsc.SupplyChainEnv(info, num_envs=n, mode="exact_f64", auto_reset=False, **okw), dem, lts, a)
+    assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
