@@ -552,3 +552,24 @@ def test_runtime_instantiated_kernel_matches_the_runtime_topology_kernel(mode):
     o4, r4, d4 = b.rollout(20)
     assert torch.equal(d3, d4)
     assert torch.allclose(r3, r4, rtol=10 * tol[0], atol=1e-1 if mode == "fast_f32" else 1e-5)
+
+
+@pytest.mark.parametrize("env_id,kw", [("supplychain-ntom-v0", {}), ("supplychain-ntom-v0", {"nodes_per_echelon": [2, 3, 2, 4], "num_products": 3,
+                                                                                             "avg_leadtime": 3, "max_leadtime": 3}),
+                                       ("supplychain-v0", {})])
+@pytest.mark.parametrize("mode", ["mixed", "fast_f32"])
+def test_chunked_rollouts_equal_one_rollout_bit_for_bit(env_id, kw, mode):
+    """The env state written back to HBM at the end of a launch carries everything: 60 periods in launches of 37 + 1 + 22
+    (auto-reset inside, Philox demand, an odd number of envs) are bit-identical to one launch of 60."""
+    n, T = 1000 + 13, 60
+    a = gsc.make(env_id, num_envs=n, seed=3, mode=mode, auto_reset=True, total_time_steps=25, **kw)
+    b = gsc.make(env_id, num_envs=n, seed=3, mode=mode, auto_reset=True, total_time_steps=25, **kw)
+    assert torch.equal(a.reset(), b.reset())
+    acts = torch.rand(T, n, a.n_actions, device="cuda") * 2.4 - 1.2
+    o1, r1, d1 = a.rollout(T, acts)
+    parts = [b.rollout(37, acts[:37]), b.rollout(1, acts[37:38]), b.rollout(22, acts[38:])]
+    o2, r2, d2 = (torch.cat([p[i] for p in parts]) for i in range(3))
+    assert torch.equal(d1, d2) and torch.equal(r1, r2) and torch.equal(o1, o2)
+    assert torch.equal(a.get_state(), b.get_state())
+    sa, sb = a.return_stats(), b.return_stats()             # count / min / max exact; the sums are atomics in launch order
+    assert sa[0] == sb[0] and torch.equal(sa[3:], sb[3:]) and torch.allclose(sa[1:3], sb[1:3], rtol=1e-12, atol=0)
