@@ -588,10 +588,18 @@ int scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uin
     unsigned char* hb = (unsigned char*)h->bounce;
     unsigned char* d = (unsigned char*)h->stage;
     memcpy(hb, actions, n * A * es);
-    SCG_CUDA(cudaMemcpyAsync(d, hb, n * A * es, cudaMemcpyHostToDevice, h->hstream));
-    rc = dispatch(h, SC_OP_ROLLOUT, 1, nullptr, d, obs ? d + b_act : nullptr, d + b_act + b_obs, d + b_act + b_obs + b_rew, h->hstream);
-    if (rc != SCG_OK) return rc;
-    SCG_CUDA(cudaMemcpyAsync(hb + b_act, d + b_act, b_obs + b_rew + b_done, cudaMemcpyDeviceToHost, h->hstream));
+    if (total <= ((size_t)16 << 10)) {
+        // a handful of envs: the kernel reads the actions from and writes its results to the pinned buffer directly
+        // (unified addressing makes cudaMallocHost memory device-accessible), so a step is one launch and one
+        // synchronisation -- no copy calls at all
+        rc = dispatch(h, SC_OP_ROLLOUT, 1, nullptr, hb, obs ? hb + b_act : nullptr, hb + b_act + b_obs, hb + b_act + b_obs + b_rew, h->hstream);
+        if (rc != SCG_OK) return rc;
+    } else {
+        SCG_CUDA(cudaMemcpyAsync(d, hb, n * A * es, cudaMemcpyHostToDevice, h->hstream));
+        rc = dispatch(h, SC_OP_ROLLOUT, 1, nullptr, d, obs ? d + b_act : nullptr, d + b_act + b_obs, d + b_act + b_obs + b_rew, h->hstream);
+        if (rc != SCG_OK) return rc;
+        SCG_CUDA(cudaMemcpyAsync(hb + b_act, d + b_act, b_obs + b_rew + b_done, cudaMemcpyDeviceToHost, h->hstream));
+    }
     SCG_CUDA(cudaStreamSynchronize(h->hstream));
     if (obs) memcpy(obs, hb + b_act, n * O * es);
     memcpy(reward, hb + b_act + b_obs, n * es);
