@@ -16,10 +16,10 @@ namespace scg {
 // PF = how many weeks ahead the action row of the 4-level fast path is requested (memory-level parallelism:
 // one 16-byte load per lane per week would leave only ~8 KB in flight per SM).
 #ifndef SCG_BG_PF
-#define SCG_BG_PF 4
+#define SCG_BG_PF 2
 #endif
 #ifndef SCG_BG_MINB
-#define SCG_BG_MINB 3
+#define SCG_BG_MINB 4
 #endif
 constexpr int BG_PF = SCG_BG_PF;
 
