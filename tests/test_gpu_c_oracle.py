@@ -273,3 +273,80 @@ def test_exact_f64_bit_exact_on_random_layered_chains_with_tight_factories(seed)
     ref = _oracle_run(cc, dem, lts, a, canonical=False)
     got = _gpu_run(gsc.SupplyChainEnv(info, num_envs=n, mode="exact_f64", auto_reset=False, **okw), dem, lts, a)
     assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on numpy uint64 arrays holding 32-bit words: the generator of
+    csrc/scg_common.cuh restated on the host."""
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) & MASK for x in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0) & MASK, np.uint64(k1) & MASK
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0, c1, c2, c3
+
+
+def test_beergame_in_kernel_generators_are_the_documented_philox_streams():
+    """beergame-v2 with randint demand / delays (beergame2_env.py:86-92, hi exclusive) generated IN the kernel: demand and
+    delay of (env, episode, week) are words x and y of the Philox block keyed (seed, global env, episode, week, stream 4),
+    mapped by multiply-shift.  The tables rebuilt on the host with that rule drive the C oracle to the same trajectories,
+    over two episodes with auto-reset and a non-zero first_env."""
+    from oracle.c_oracle import CBeerGameOracle
+    n, T, seed, first = 257, 35, 0x1234567890ABCDEF, 1000
+    env = gsc.BeerGameEnv2(customer_demand=(0, 16), shipment_delays=(0, 5), num_envs=n, seed=seed, auto_reset=True, first_env=first)
+    env.reset()
+    acts = np.random.RandomState(1).randint(0, 30, size=(2 * T, n, 4)).astype(np.int32)
+    o, r, d = env.rollout(2 * T, torch.from_numpy(acts).cuda())
+    o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy().astype(bool)
+    genv = np.arange(first, first + n, dtype=np.uint64)
+    ora = CBeerGameOracle(version=2, weeks=T)
+    for ep in range(2):
+        dem, dl = np.empty((n, T), np.int32), np.empty((n, T), np.int32)
+        for w in range(1, T + 1):
+            c1 = ((genv >> np.uint64(32)) & np.uint64(0xFFFF)) | np.uint64(4 << 28)          # block 0, stream STREAM_BG_DEMAND = 4
+            # episode counter: creating the handle resets once (episode 0), env.reset() above started episode 1
+            x, y, _, _ = _philox4x32_10(genv, c1, np.full(n, ep + 1, np.uint64), np.full(n, w, np.uint64), seed & 0xFFFFFFFF, seed >> 32)
+            dem[:, w - 1] = (x * np.uint64(16)) >> np.uint64(32)                               # lo + umulhi(word, hi - lo)
+            dl[:, w - 1] = (y * np.uint64(5)) >> np.uint64(32)
+        assert dem.min() == 0 and dem.max() == 15 and dl.min() == 0 and dl.max() == 4
+        for e in range(0, n, 5):
+            ora.reset(dem[e], dl[e])
+            for t in range(T):
+                obs, rew, done, _ = ora.step(acts[ep * T + t, e])
+                k = ep * T + t
+                assert rew == r[k, e] and done == d[k, e], (ep, e, t)
+                if not done:                                   # with auto-reset the obs returned with done is the next episode's first
+                    assert np.array_equal(obs, o[k, e])
+
+
+def test_supplychain_in_kernel_uniform_demand_is_the_documented_philox_stream():
+    """ntom, uniform demand U{0..400} generated in the kernel: demand (row t, retailer-product rp) of (env, episode) is
+    word rp & 3 of the Philox block keyed (seed, global env, episode, row t, stream 0, block rp >> 2), mapped by
+    multiply-shift onto lo .. hi inclusive.  Read back from the first R*P observation entries of a fast_f64 rollout."""
+    n, T, seed, first = 193, 40, 77, 5000
+    env = gsc.make("supplychain-ntom-v0", num_envs=n, mode="fast_f64", seed=seed, first_env=first, auto_reset=True, total_time_steps=25)
+    o0 = env.reset()
+    o, r, d = env.rollout(T)
+    RP, lo, span = 6, 0, 400
+    seen = np.concatenate([o0[None].cpu().numpy(), o.cpu().numpy()])[..., :RP]        # obs after period t shows demand row t
+    seen = np.rint((seen + 1) / 2 * span + lo).astype(np.int64)                       # [T+1, n, RP]
+    genv = np.arange(first, first + n, dtype=np.uint64)
+    done = d.cpu().numpy().astype(bool)
+    episode, t = np.full(n, 1, np.uint64), np.zeros(n, np.uint64)                     # create() reset once (episode 0), reset() -> 1
+    for k in range(T + 1):
+        for b in range(2):
+            c1 = ((genv >> np.uint64(32)) & np.uint64(0xFFFF)) | (np.uint64(b) << np.uint64(16))          # stream 0
+            words = _philox4x32_10(genv, c1, episode, t, seed, 0)
+            for j in range(4):
+                rp = 4 * b + j
+                if rp < RP:
+                    want = (words[j] * np.uint64(span + 1)) >> np.uint64(32)
+                    assert np.array_equal(want.astype(np.int64) + lo, seen[k, :, rp]), (k, rp)
+        if k < T:
+            t = t + np.uint64(1)
+            fin = done[k]
+            episode = np.where(fin, episode + np.uint64(1), episode)
+            t = np.where(fin, np.uint64(0), t)
