@@ -350,3 +350,45 @@ def test_supplychain_in_kernel_uniform_demand_is_the_documented_philox_stream():
             fin = done[k]
             episode = np.where(fin, episode + np.uint64(1), episode)
             t = np.where(fin, np.uint64(0), t)
+
+
+def test_supplychain_v0_in_kernel_demand_and_leadtimes_drive_the_oracle_to_the_same_trajectory():
+    """supplychain-v0 (the reference's demo chain: stochastic lead times avg 2 / max 4, K = 14 values per period) with BOTH
+    generators in the kernel.  Host restatement: demand as above (stream 0); lead time k of period t = 1 + #{j < 3 : word >=
+    ceil(CDF_Poisson(1)(j) * 2^32)} with word (k & 3) of block (k >> 2), stream 1, row t (clip(1 + Poisson(avg-1), 1, max),
+    supplychain_env.py:670-672).  The C oracle fed those tables reproduces every reward of the fp64 ring kernel."""
+    import math
+    n, seed, first = 130, 2024, 300
+    info, kw = presets.main_demo_chain()
+    okw = {k: v for k, v in kw.items() if k not in ("seed", "build_info")}
+    T = okw["total_time_steps"]
+    cc = CSupplyChainOracle(info, **okw)
+    env = gsc.make("supplychain-v0", num_envs=n, mode="fast_f64", seed=seed, first_env=first, auto_reset=False)
+    K, RP = cc.n_leadtimes, cc.n_retailers * cc.P
+    lo, hi = okw["demand_range"]
+    assert K == 14 and env.scg_info.n_leadtimes == K
+    genv = np.arange(first, first + n, dtype=np.uint64)
+    ep = np.full(n, 1, np.uint64)                                   # create() -> episode 0, reset() below -> 1
+
+    def words(stream, row, count):
+        out = np.empty((n, count), np.uint64)
+        for b in range((count + 3) // 4):
+            c1 = ((genv >> np.uint64(32)) & np.uint64(0xFFFF)) | (np.uint64(b) << np.uint64(16)) | (np.uint64(stream) << np.uint64(28))
+            w4 = _philox4x32_10(genv, c1, ep, np.full(n, row, np.uint64), seed, 0)
+            for j in range(4):
+                if 4 * b + j < count:
+                    out[:, 4 * b + j] = w4[j]
+        return out
+    dem = np.stack([(words(0, t, RP) * np.uint64(hi - lo + 1)) >> np.uint64(32) for t in range(T + 1)], axis=1).astype(np.int32) + lo
+    cdf, p, thr = 0.0, math.exp(-1.0), []
+    for j in range(3):
+        cdf += p; thr.append(math.ceil(cdf * 4294967296.0)); p *= 1.0 / (j + 1)
+    lts = np.stack([1 + sum((words(1, t, K) >= np.uint64(th)).astype(np.int32) for th in thr) for t in range(1, T + 1)], axis=1).astype(np.int32)
+    assert lts.min() == 1 and lts.max() == 4 and abs(lts.mean() - 2.0) < 0.05
+    a = np.random.RandomState(3).uniform(-1, 1, size=(T, n, cc.n_actions)).astype(np.float32)
+    ref = _oracle_run(cc, dem.reshape(n, T + 1, cc.n_retailers, cc.P), lts, a, canonical=True)
+    o0 = env.reset()
+    o, r, d = env.rollout(T, torch.from_numpy(a).double().cuda())
+    assert np.allclose(r.cpu().numpy(), ref[1], rtol=1e-11, atol=1e-9)
+    assert np.abs(np.concatenate([o0[None].cpu().numpy(), o.cpu().numpy()]) - ref[0]).max() <= 1e-11
+    assert np.array_equal(d.cpu().numpy().astype(bool), ref[2])
