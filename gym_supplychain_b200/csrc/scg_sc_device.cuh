@@ -164,6 +164,19 @@ template <> __device__ __forceinline__ double relu_loose<double>(double x) {
 #endif
 }
 
+// v, or "loosely" zero when d > 0: the double flavour tests and clears the high word only (one integer compare and one
+// select instead of a compare on the FP64 pipe and two selects).  What stays behind is a non-negative denormal, and a
+// positive denormal d does not count as positive -- both harmless for a capacity that is only ever subtracted from amounts.
+template <class Real> __device__ __forceinline__ Real clear_if_positive_loose(Real v, Real d);
+template <> __device__ __forceinline__ float clear_if_positive_loose<float>(float v, float d) { return d > 0.0f ? 0.0f : v; }
+template <> __device__ __forceinline__ double clear_if_positive_loose<double>(double v, double d) {
+#if SCG_LOOSE_RELU
+    return __hiloint2double(__double2hiint(d) > 0 ? 0 : __double2hiint(v), __double2loint(v));
+#else
+    return d > 0.0 ? 0.0 : v;
+#endif
+}
+
 // everything relu_loose can leave behind is below this; no real quantity of the simulation is
 template <class Real> __device__ __forceinline__ constexpr Real loose_zero() { return sizeof(Real) == 8 ? (Real)1e-300 : (Real)0; }
 
@@ -485,7 +498,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 over_ship += ex;
                                 send[i] -= ex;
                                 out[i] = send[i];
-                                room[i] = d > (Real)0 ? (Real)0 : room[i];
+                                room[i] = clear_if_positive_loose<Real>(room[i], d);
                             } else if (send[i] > loose_zero<Real>() && send[i] > room[i]) {
                                 // a factory's capacity can be NEGATIVE here (after a clip of an earlier product the
                                 // reference subtracts raw-material units, F4a), so this `send > 0` decides a whole

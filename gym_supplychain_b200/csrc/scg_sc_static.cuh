@@ -135,13 +135,41 @@ __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real
         pr[1] = c01 ? cpd[0] : (RawT)-1;
     } else if constexpr (D == 3) {
         const bool c01 = r[0] <= r[1], c02 = r[0] <= r[2], c12 = r[1] <= r[2];
-        auto prev_of = [&](bool bj, bool bk, bool bjk, RawT wj, RawT wk) {
-            const RawT cand = (bk && (!bj || bjk)) ? wk : wj;
-            return (bj || bk) ? cand : (RawT)-1;
-        };
-        pr[0] = prev_of(!c01, !c02, c12, cpd[1], cpd[2]);
-        pr[1] = prev_of(c01, !c12, c02, cpd[0], cpd[2]);
-        pr[2] = prev_of(c02, c12, c01, cpd[0], cpd[1]);
+        if constexpr (sizeof(RawT) == 4) {
+            // only the VALUE of the predecessor matters: with both others before i it is the larger of the two
+            // (one FMNMX), so three selects and no predicate logic.  "None" must stay a separate case: the start
+            // cut (raw -1) precedes every destination even when an out-of-range action lies below it.
+            auto prev_of = [&](bool bj, bool bk, RawT wj, RawT wk) {
+                const RawT both = fmaxf(wj, wk);
+                return bj ? (bk ? both : wj) : (bk ? wk : (RawT)-1);
+            };
+            pr[0] = prev_of(!c01, !c02, cpd[1], cpd[2]);
+            pr[1] = prev_of(c01, !c12, cpd[0], cpd[2]);
+            pr[2] = prev_of(c02, c12, cpd[0], cpd[1]);
+        } else {                                                             // no fp64 max instruction on sm_100
+            auto prev_of = [&](bool bj, bool bk, bool bjk, RawT wj, RawT wk) {
+                const RawT cand = (bk && (!bj || bjk)) ? wk : wj;
+                return (bj || bk) ? cand : (RawT)-1;
+            };
+            pr[0] = prev_of(!c01, !c02, c12, cpd[1], cpd[2]);
+            pr[1] = prev_of(c01, !c12, c02, cpd[0], cpd[2]);
+            pr[2] = prev_of(c02, c12, c01, cpd[0], cpd[1]);
+        }
+    } else if constexpr (sizeof(RawT) == 4) {
+        // any D, fp32 actions: the predecessor's value is the largest capped action of those before i (a select and an
+        // FMNMX per pair); "nobody before i" stays a separate case, as above
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const RawT none = __int_as_float((int)0xff800000u);          // -inf
+            RawT m = none;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (j == i) continue;
+                const bool before = (j < i) ? (r[j] <= r[i]) : (r[j] < r[i]);
+                m = fmaxf(m, before ? cpd[j] : none);
+            }
+            pr[i] = m == none ? (RawT)-1 : m;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
