@@ -81,6 +81,7 @@ PROTOTYPES = [
     ("scg_get_info", C.c_int, [_vp, _vp, _vp]),
     ("scg_state_layout", C.c_int, [_vp, C.POINTER(C.c_int64 * 8)]),
     ("scg_launch_count", C.c_int64, [_vp]),
+    ("scg_status", C.c_int, [_vp, C.c_int32]),
 ]
 
 _lib = None

@@ -52,7 +52,9 @@ struct ScgEnv {
     void* state_blob = nullptr;
     size_t state_bytes = 0;
     int64_t layout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double* stats = nullptr;        // [5] live  + [5] init pattern
+    double* stats = nullptr;        // [5] live  + [5] init pattern (+ the error word behind them)
+    int* err = nullptr;             // sticky SCG_ERR_* bits raised by kernels (pinned, device-mapped; scg_status)
+    cudaEvent_t ev_user = nullptr;  // last device-pointer call on a caller stream: the *_host calls wait for it
     double* info_buf = nullptr;     // build_info: [16*P][n]
     const int32_t* inj_demand = nullptr;
     const int32_t* inj_leadtimes = nullptr;
@@ -237,6 +239,11 @@ static int alloc_stats(ScgEnv* h) {
     SCG_CUDA(cudaMalloc(&h->stats, 10 * sizeof(double)));
     const double init[10] = {0, 0, 0, 1e300, -1e300, 0, 0, 0, 1e300, -1e300};
     SCG_CUDA(cudaMemcpy(h->stats, init, sizeof(init), cudaMemcpyHostToDevice));
+    // the error word lives in pinned, device-mapped host memory: kernels only touch it when something IS wrong, and the
+    // host reads it without a copy
+    SCG_CUDA(cudaHostAlloc((void**)&h->err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->err = 0;
+    SCG_CUDA(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
     return SCG_OK;
 }
 
@@ -249,7 +256,7 @@ static int sc_dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask
     r.inj_demand = h->inj_demand; r.inj_leadtimes = h->inj_leadtimes;
     r.key = h->key; r.first_env = h->opt.first_env; r.auto_reset = h->opt.auto_reset;
     r.op = op; r.n_steps = n_steps; r.reset_mask = mask; r.actions = actions; r.obs = obs; r.reward = reward; r.done = done;
-    r.stream = stream;
+    r.stream = stream; r.err = h->err;
     ++h->launches;
     if (op == SC_OP_ROLLOUT && h->variant == SC_VARIANT_JIT) {
         if (sc_jit_run(&h->jit, r) == SCG_OK) return SCG_OK;
@@ -265,15 +272,29 @@ static int bg_dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask
     r.sp = h->bsp; r.st = h->bst; r.inj_demand = h->inj_demand; r.inj_delays = h->inj_leadtimes;
     r.key = h->key; r.first_env = h->opt.first_env; r.auto_reset = h->opt.auto_reset;
     r.op = op; r.n_steps = n_steps; r.reset_mask = mask;
-    r.actions = (const int32_t*)actions; r.obs = (int32_t*)obs; r.reward = (int32_t*)reward; r.done = done; r.stream = stream;
+    r.actions = (const int32_t*)actions; r.obs = (int32_t*)obs; r.reward = (int32_t*)reward; r.done = done; r.stream = stream; r.err = h->err;
     ++h->launches;
     return bg_run(r);
 }
 
 static int dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask, const void* actions, void* obs, void* reward,
                     unsigned char* done, cudaStream_t stream) {
-    return h->family == 0 ? sc_dispatch(h, op, n_steps, mask, actions, obs, reward, done, stream)
-                          : bg_dispatch(h, op, n_steps, mask, actions, obs, reward, done, stream);
+    const int rc = h->family == 0 ? sc_dispatch(h, op, n_steps, mask, actions, obs, reward, done, stream)
+                                  : bg_dispatch(h, op, n_steps, mask, actions, obs, reward, done, stream);
+    // work enqueued on a CALLER stream: the *_host entry points (own non-blocking streams) order themselves behind it
+    if (rc == SCG_OK && stream != h->hstream && h->ev_user) SCG_CUDA(cudaEventRecord(h->ev_user, stream));
+    return rc;
+}
+
+// Sticky error bits raised by kernels -> message + SCG_ESTATE.  The caller has synchronised the work in question.
+static int report_device_errors(ScgEnv* h) {
+    const int e = *(volatile int*)h->err;
+    if (e == 0) return SCG_OK;
+    set_error("device-side checks failed:%s%s%s",
+              (e & 1) ? " an injected lead time is outside [1, max_leadtime] (clamped);" : "",
+              (e & 2) ? " an in-transit queue overflowed its capacity (entry dropped);" : "",
+              (e & 4) ? " an injected beer-game delay is outside [0, ring depth] (clamped);" : "");
+    return SCG_ESTATE;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -425,6 +446,8 @@ void scg_destroy(ScgHandle h) {
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
     sc_jit_free(h->jit);
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
+    if (h->err) cudaFreeHost(h->err);
     if (h->bounce) cudaFreeHost(h->bounce);
     cudaFree(h->info_buf); cudaFree(h->stage); cudaFree(h->state_blob); cudaFree(h->spec_blob); cudaFree(h->bg_blob); cudaFree(h->stats);
     delete h;
@@ -443,7 +466,11 @@ int scg_seed(ScgHandle h, uint64_t seed) {
     if (rc != SCG_OK) return rc;
     h->key = key_from_seed(seed);
     int* ep = h->family == 0 ? (is_f64(h->opt.mode) ? h->st64.episode : h->st32.episode) : h->bst.episode;
+    // a rare, host-synchronous call: everything enqueued on ANY stream (the caller's, the handle's own non-blocking ones)
+    // finishes with the old key and episode counters, and the counters are rewritten before anything new can start
+    SCG_CUDA(cudaDeviceSynchronize());
     SCG_CUDA(cudaMemset(ep, 0xFF, (size_t)h->opt.n_envs * 4));
+    SCG_CUDA(cudaDeviceSynchronize());
     return SCG_OK;
 }
 
@@ -506,12 +533,13 @@ int scg_reset_host(ScgHandle h, const uint8_t* mask, void* obs) {
     rc = ensure_stage(h, b_obs + b_mask);
     if (rc != SCG_OK) return rc;
     unsigned char* d = (unsigned char*)h->stage;
+    SCG_CUDA(cudaStreamWaitEvent(h->hstream, h->ev_user, 0));
     if (mask) SCG_CUDA(cudaMemcpyAsync(d + b_obs, mask, n, cudaMemcpyHostToDevice, h->hstream));
     rc = dispatch(h, SC_OP_RESET, 0, mask ? d + b_obs : nullptr, nullptr, obs ? d : nullptr, nullptr, nullptr, h->hstream);
     if (rc != SCG_OK) return rc;
     if (obs) SCG_CUDA(cudaMemcpyAsync(obs, d, n * h->info.n_obs * es, cudaMemcpyDeviceToHost, h->hstream));
     SCG_CUDA(cudaStreamSynchronize(h->hstream));
-    return SCG_OK;
+    return report_device_errors(h);
 }
 
 int scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, void* reward, uint8_t* done) {
@@ -534,6 +562,7 @@ int scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, voi
     const size_t b_set = b_act + b_obs + b_rew + b_done;
     rc = ensure_stage(h, 2 * b_set);
     if (rc != SCG_OK) return rc;
+    SCG_CUDA(cudaStreamWaitEvent(h->hstream, h->ev_user, 0));
     size_t i = 0;
     for (size_t s0 = 0; s0 < (size_t)T; s0 += chunk, ++i) {
         const int b = (int)(i & 1);
@@ -562,7 +591,7 @@ int scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, voi
     SCG_CUDA(cudaStreamSynchronize(h->s_out));
     SCG_CUDA(cudaStreamSynchronize(h->hstream));
     SCG_CUDA(cudaStreamSynchronize(h->s_in));
-    return SCG_OK;
+    return report_device_errors(h);
 }
 
 int scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uint8_t* done) {
@@ -587,6 +616,7 @@ int scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uin
     }
     unsigned char* hb = (unsigned char*)h->bounce;
     unsigned char* d = (unsigned char*)h->stage;
+    SCG_CUDA(cudaStreamWaitEvent(h->hstream, h->ev_user, 0));
     memcpy(hb, actions, n * A * es);
     if (total <= ((size_t)16 << 10)) {
         // a handful of envs: the kernel reads the actions from and writes its results to the pinned buffer directly
@@ -604,7 +634,7 @@ int scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uin
     if (obs) memcpy(obs, hb + b_act, n * O * es);
     memcpy(reward, hb + b_act + b_obs, n * es);
     memcpy(done, hb + b_act + b_obs + b_rew, n);
-    return SCG_OK;
+    return report_device_errors(h);
 }
 
 int scg_get_state(ScgHandle h, void* blob, void* stream) {
@@ -622,6 +652,7 @@ int scg_set_state(ScgHandle h, const void* blob, void* stream) {
     int rc = set_device(h);
     if (rc != SCG_OK) return rc;
     SCG_CUDA(cudaMemcpyAsync(h->state_blob, blob, h->state_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    SCG_CUDA(cudaEventRecord(h->ev_user, (cudaStream_t)stream));
     return SCG_OK;
 }
 
@@ -654,5 +685,15 @@ int scg_state_layout(ScgHandle h, int64_t offsets[8]) {
 }
 
 int64_t scg_launch_count(ScgHandle h) { return h ? h->launches : 0; }
+
+int scg_status(ScgHandle h, int32_t clear) {
+    if (check_handle(h) != SCG_OK) return SCG_EINVAL;
+    int rc = set_device(h);
+    if (rc != SCG_OK) return rc;
+    SCG_CUDA(cudaDeviceSynchronize());
+    rc = report_device_errors(h);
+    if (clear) *h->err = 0;
+    return rc;
+}
 
 }  // extern "C"

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                                                  const int32_t* __restrict__ inj_delays, RngKey key, long long first_env,
                                                  int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
                                                  int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
-                                                 int32_t* __restrict__ reward, unsigned char* __restrict__ done) {
+                                                 int32_t* __restrict__ reward, unsigned char* __restrict__ done, int* err) {
     const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n = st.n;
     const int L = STATIC ? LMAX : sp.L;
@@ -122,7 +122,13 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
             if (inj_demand) dem = inj_demand[(long long)(week - 1) * n + env];
             else if (rnd_dem) dem = uniform_int(wk.x, sp.dem_lo, (unsigned)(sp.dem_hi - sp.dem_lo));
             else dem = s_dem[week - 1];
-            if (inj_delays) delay = inj_delays[(long long)(week - 1) * n + env];
+            if (inj_delays) {
+                delay = inj_delays[(long long)(week - 1) * n + env];
+                if (delay < 0 || delay > RING) {          // would land outside the in-transit ring: clamp and flag (scg_status)
+                    if ((*(volatile int*)err & 4) == 0) atomicOr(err, 4);
+                    delay = delay < 0 ? 0 : RING;
+                }
+            }
             else if (rnd_del) delay = uniform_int(wk.y, sp.del_lo, (unsigned)(sp.del_hi - sp.del_lo));
             else delay = s_del[week - 1];
             // 2. fill orders (:79-89)
@@ -219,7 +225,7 @@ int bg_run(const BgRun& r) {
 #define SCG_BG_LAUNCH(LM, RM, ST)                                                                              \
     bg_kernel<LM, RM, ST><<<blocks, threads, smem, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,      \
                                                             r.first_env, r.auto_reset, n_steps, r.reset_mask,   \
-                                                            do_reset, r.actions, r.obs, r.reward, r.done)
+                                                            do_reset, r.actions, r.obs, r.reward, r.done, r.err)
     if (r.sp.L == 4 && r.sp.ring == 2) SCG_BG_LAUNCH(4, 2, true);
     else if (r.sp.L == 4 && r.sp.ring == 4) SCG_BG_LAUNCH(4, 4, true);
     else SCG_BG_LAUNCH(8, 8, false);

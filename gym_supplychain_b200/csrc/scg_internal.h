@@ -57,6 +57,7 @@ struct ScRun {
     void* reward;
     unsigned char* done;
     cudaStream_t stream;
+    int* err;                   // device word of sticky SCG_ERR_* bits (scg_status)
 };
 
 // Implemented in scg_sc_f32.cu / scg_sc_f64.cu
@@ -105,6 +106,7 @@ struct BgRun {
     int op; int n_steps; const unsigned char* reset_mask;
     const int32_t* actions; int32_t* obs; int32_t* reward; unsigned char* done;
     cudaStream_t stream;
+    int* err;
 };
 int bg_run(const BgRun& r);
 

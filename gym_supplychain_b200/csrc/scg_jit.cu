@@ -163,6 +163,13 @@ void pack_consts(const ScHostSpec& hs, int S, int F, int W, int R, int ML, Packe
             for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) init[(size_t)i * ML + hs.itime[k] - 1] += (Real)hs.iamt[k];
         pk.put<Real>("init_slot", init.data(), init.size());
     }
+    const std::vector<double> qs = sc_ring_scales(hs);
+    const bool fixed_ring = sizeof(Real) == 8 && !hs.stochL;
+    {
+        std::vector<Real> a(NP), b(NP);
+        for (int i = 0; i < NP; ++i) { a[i] = (Real)qs[i]; b[i] = (Real)(1.0 / qs[i]); }
+        pk.put<Real>("q_scale", a.data(), NP); pk.put<Real>(nullptr, b.data(), NP);
+    }
     {
         const std::vector<unsigned long long> thr = sc_leadtime_thresholds(hs);
         std::vector<unsigned long long> t((size_t)ML);
@@ -172,9 +179,10 @@ void pack_consts(const ScHostSpec& hs, int S, int F, int W, int R, int ML, Packe
     {
         std::vector<float> a(NP), b(NP), c(NP);
         for (int i = 0; i < NP; ++i) {
+            const double q = fixed_ring ? 1.0 / qs[i] : 1.0;
             a[i] = (float)(1.0 / hs.cap[i]);
-            b[i] = (float)(1.0 / hs.max_ship[i]);
-            c[i] = (float)(1.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
+            b[i] = (float)(hs.max_ship[i] > 0 ? q / hs.max_ship[i] : 0.0);
+            c[i] = (float)(hs.max_ship[i] > 0 ? q / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))) : 0.0);
         }
         pk.put<float>("obs_stock", a.data(), NP); pk.put<float>(nullptr, b.data(), NP); pk.put<float>("obs_last", c.data(), NP);
     }
@@ -228,6 +236,16 @@ bool packer_matches() {
     fill(hs.dlo, P); fill(hs.dhi, P);
     for (int p = 0; p < P; ++p) hs.dhi[p] += 100.0;
     hs.dkind.assign(P, 0);
+    {   // layered full-bipartite edges (sc_ring_scales walks them)
+        const int cnt[4] = {S, F, W, R}, base[4] = {0, S, S + F, S + F + W};
+        hs.ebeg.assign(N + 1, 0);
+        for (int e = 0; e < 4; ++e)
+            for (int j = 0; j < cnt[e]; ++j) {
+                const int n = base[e] + j;
+                hs.ebeg[n + 1] = hs.ebeg[n] + (e < 3 ? cnt[e + 1] : 0);
+                for (int i = 0; e < 3 && i < cnt[e + 1]; ++i) hs.edst.push_back(base[e + 1] + i);
+            }
+    }
     hs.ibeg.assign(NP + 1, 0);
     for (int i = 0; i < NP; ++i) {
         hs.ibeg[i + 1] = hs.ibeg[i] + 1;
@@ -451,7 +469,7 @@ int sc_jit_run(ScJit** cache, const ScRun& r) {
     }
     const bool f64 = r.mode != SCG_MODE_FAST_F32;
     const long long n = f64 ? reinterpret_cast<const ScState<double>*>(r.state)->n : reinterpret_cast<const ScState<float>*>(r.state)->n;
-    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
+    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
     int n_steps = r.n_steps;
     const void* actions = r.actions;
     void* obs = r.obs; void* reward = r.reward; unsigned char* done = r.done;

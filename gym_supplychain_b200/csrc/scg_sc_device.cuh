@@ -67,7 +67,19 @@ struct ScInputs {
     RngKey key;
     long long first_env;
     int auto_reset;
+    int* err;                       // sticky SCG_ERR_* bits of the handle (scg_status); never null
 };
+
+// Sticky error bits a kernel can raise (read back by scg_status / the *_host calls).
+enum : int { SCG_ERR_LEADTIME_RANGE = 1, SCG_ERR_QUEUE_OVERFLOW = 2, SCG_ERR_DELAY_RANGE = 4 };
+__device__ __forceinline__ void raise_error(int* err, int bit) {
+    if ((*(volatile int*)err & bit) == 0) atomicOr(err, bit);
+}
+// An injected lead time outside [1, max_leadtime] would index past the ring / overfill a queue: clamp it and flag it.
+__device__ __forceinline__ int checked_leadtime(int lt, int maxL, int* err) {
+    if (lt < 1 || lt > maxL) { raise_error(err, SCG_ERR_LEADTIME_RANGE); lt = lt < 1 ? 1 : maxL; }
+    return lt;
+}
 
 // Global env state, env-minor ("SoA"): element i of env e lives at base[i*n + e].
 template <class Real>
@@ -120,7 +132,7 @@ template <class Real>
 __device__ __forceinline__ int sc_leadtime(const ScDevSpec<Real>& sp, const ScInputs& in, long long n_envs, long long env,
                                            unsigned episode, int t, int k) {
     if (!sp.stochL) return sp.avgL;                                         // supplychain_env.py:724
-    if (in.inj_leadtimes) return in.inj_leadtimes[((long long)(t - 1) * sp.K + k) * n_envs + env];
+    if (in.inj_leadtimes) return checked_leadtime(in.inj_leadtimes[((long long)(t - 1) * sp.K + k) * n_envs + env], sp.maxL, in.err);
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
     Philox4 b = rng_block(in.key, genv, episode, (unsigned)t, STREAM_LEADTIME, (unsigned)(k >> 2));
     const unsigned long long word = pick_word(b, k & 3);
@@ -269,9 +281,9 @@ struct RingGlobal {
 struct HeapGlobal {
     static constexpr bool kTwoPhase = false;   // reference order: node by node
     static constexpr bool kExactObs = true;
-    double* stock; int* hlen; int* htime; double* hamt; long long n; int cap;
-    __device__ __forceinline__ HeapGlobal(double* stock_, int* hlen_, int* htime_, double* hamt_, long long stride, int cap_)
-        : stock(stock_), hlen(hlen_), htime(htime_), hamt(hamt_), n(stride), cap(cap_) {}
+    double* stock; int* hlen; int* htime; double* hamt; long long n; int cap; int* err;
+    __device__ __forceinline__ HeapGlobal(double* stock_, int* hlen_, int* htime_, double* hamt_, long long stride, int cap_, int* err_)
+        : stock(stock_), hlen(hlen_), htime(htime_), hamt(hamt_), n(stride), cap(cap_), err(err_) {}
     __device__ __forceinline__ double get_stock(int np) const { return stock[(long long)np * n]; }
     __device__ __forceinline__ void set_stock(int np, double v) { stock[(long long)np * n] = v; }
     __device__ __forceinline__ int& len(int np) { return hlen[(long long)np * n]; }
@@ -290,7 +302,9 @@ struct HeapGlobal {
     }
     __device__ __forceinline__ void push_item(int np, int when, double amount) {
         int L = len(np);
-        if (L >= cap) return;                  // cannot happen: cap = n_src*maxL + n_init (host-checked)
+        // cap = n_src*(maxL+1) + n_init holds every legal trajectory (lead times are range-checked on read); if a
+        // caller-built state blob (scg_set_state) overfills a queue the entry is dropped and the handle flagged
+        if (L >= cap) { raise_error(err, SCG_ERR_QUEUE_OVERFLOW); return; }
         len(np) = L + 1;
         sift_down(np, 0, L, when, amount);
     }
@@ -604,11 +618,13 @@ __device__ __forceinline__ void sc_obs_ring(const Tp& tp, const ScDevSpec<Real>&
         for (int p = 0; p < P; ++p) ow.put(o++, obs_norm<Real>(pp.get_stock(n * P + p) / tp.cap(n, p)));
         for (int p = 0; p < P; ++p) {
             const int np = n * P + p;
+            // a (node, product) nothing can be shipped to (max_ship == 0) has an empty queue: zeros, like the
+            // reference's empty-heap branch (:438-439), not 0/0
             const Real ms = tp.max_ship(n, p);
-            for (int k = 0; k + 1 < L; ++k) ow.put(o++, obs_norm<Real>(pp.slot_at(np, k) / ms));
+            for (int k = 0; k + 1 < L; ++k) ow.put(o++, obs_norm<Real>(ms > (Real)0 ? pp.slot_at(np, k) / ms : (Real)0));
             Real rest = (Real)0;
             for (int k = L - 1; k < ring; ++k) rest += pp.slot_at(np, k);
-            ow.put(o++, obs_norm<Real>(rest / (ms * (Real)(tp.maxL() - (L - 1)))));
+            ow.put(o++, obs_norm<Real>(ms > (Real)0 ? rest / (ms * (Real)(tp.maxL() - (L - 1))) : (Real)0));
         }
     }
     ow.put(o++, obs_norm<Real>((Real)(tp.T() - t) / (Real)tp.T()));
@@ -770,7 +786,7 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
 
     DynTopoOps<Real> tp(sp);
     typename PipeSel<Real, MODE>::type pp = [&]() {
-        if constexpr (MODE == 1) return HeapGlobal(p_stock, p_len, p_time, p_amt, stride, sp.heapcap);
+        if constexpr (MODE == 1) return HeapGlobal(p_stock, p_len, p_time, p_amt, stride, sp.heapcap, in.err);
         else return RingGlobal<Real>(p_stock, p_slot, stride, sp.ring);
     }();
     int t = 0; unsigned episode = 0; double ep_ret = 0.0;
@@ -840,6 +856,7 @@ __global__ void __launch_bounds__(128) sc_generic_kernel(ScDevSpec<Real> sp, ScS
         if (staged_out) {
             __syncwarp();
             if (n_here > 0) warp_copy<Io>(obs + io0 * sp.O, s_obs, n_here * sp.O, lane);
+            __syncwarp();                  // the tile is rewritten by the next period's sc_write_obs
         }
     }
     if (active) {

@@ -24,6 +24,40 @@ static inline std::vector<unsigned long long> sc_leadtime_thresholds(const ScHos
     return thr;
 }
 
+// Power-of-two scales of the fixed-point lead-time ring (RingFixed, scg_sc_static.cuh), one per (node, product):
+// 2^k with k the largest exponent that keeps the biggest amount that can be in flight to that (node, product) in one
+// period below 2^32.  The bound follows from SC_Action.apply (supplychain_env.py:49-96): a SHIP amount never exceeds the
+// source's stock, which was clipped to its capacity at the start of the period (:232-240) -- divided by the processing
+// ratio at a factory (:310), capped by the edge's ship capacity elsewhere (:316-328); a SUPPLY amount is
+// action * supply_capacity (:56), given 8x headroom for out-of-range actions.  Everything else gets 2x headroom.
+static inline std::vector<double> sc_ring_scales(const ScHostSpec& hs) {
+    const int NP = hs.N * hs.P;
+    std::vector<double> bound((size_t)NP, 0.0), scale((size_t)NP, 1.0);
+    for (int n = 0; n < hs.N; ++n) {
+        const bool factory = hs.proc_cap[n] > 0;
+        for (int p = 0; p < hs.P; ++p) {
+            const int np = n * hs.P + p;
+            if (hs.sup_cap[np] > 0) bound[np] += 8.0 * hs.sup_cap[np];
+            for (int e = hs.ebeg[n]; e < hs.ebeg[n + 1]; ++e) {
+                double b = hs.cap[np];
+                if (factory && hs.ratio[np] > 0) b /= hs.ratio[np];
+                else if (hs.ecap[e] < b) b = hs.ecap[e];
+                bound[hs.edst[e] * hs.P + p] += 2.0 * (b > 0 ? b : 0.0);
+            }
+        }
+    }
+    for (int np = 0; np < NP; ++np) {
+        double init = 0.0;
+        for (int k = hs.ibeg[np]; k < hs.ibeg[np + 1]; ++k) init += std::fabs(hs.iamt[k]);
+        if (2.0 * init > bound[np]) bound[np] = 2.0 * init;
+        int k = 0;
+        if (bound[np] > 0 && std::isfinite(bound[np])) k = std::ilogb(4294967295.0 / bound[np]);
+        k = k < -60 ? -60 : (k > 60 ? 60 : k);
+        scale[np] = std::ldexp(1.0, k);
+    }
+    return scale;
+}
+
 // ---- device spec ---------------------------------------------------------------
 template <class Real>
 static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devspec_out) {
@@ -109,12 +143,16 @@ template <class Real, int S, int F, int W, int R, int P, int L, int ML, bool STO
 static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>& c) {
     memset(&c, 0, sizeof(c));
     constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
+    constexpr bool fixed_ring = sizeof(Real) == 8 && !STOCH;       // RingFixed: the fp32-I/O kernel reads obs_mid / obs_last
+    const std::vector<double> qs = sc_ring_scales(hs);
     for (int i = 0; i < NP; ++i) {
         c.cap[i] = (Real)hs.cap[i]; c.hold[i] = (Real)hs.hold[i]; c.stock0[i] = (Real)hs.stock0[i];
         c.max_ship[i] = (Real)hs.max_ship[i];
+        c.q_scale[i] = (Real)qs[i]; c.q_inv[i] = (Real)(1.0 / qs[i]);
+        const double q = fixed_ring ? 1.0 / qs[i] : 1.0;
         c.obs_stock[i] = (float)(1.0 / hs.cap[i]);
-        c.obs_mid[i] = (float)(1.0 / hs.max_ship[i]);
-        c.obs_last[i] = (float)(1.0 / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))));
+        c.obs_mid[i] = (float)(hs.max_ship[i] > 0 ? q / hs.max_ship[i] : 0.0);
+        c.obs_last[i] = (float)(hs.max_ship[i] > 0 ? q / (hs.max_ship[i] * (double)(hs.maxL - (hs.avgL - 1))) : 0.0);
         for (int k = hs.ibeg[i]; k < hs.ibeg[i + 1]; ++k) c.init_slot[i * ML + hs.itime[k] - 1] += (Real)hs.iamt[k];
     }
     for (int i = 0; i < S * P; ++i) { c.sup_cap[i] = (Real)hs.sup_cap[i]; c.sup_cost[i] = (Real)hs.sup_cost[i]; }
@@ -153,7 +191,7 @@ static int sc_launch_layered(const ScRun& r) {
     sc_fill_consts<Real, S, F, W, R, P, L, ML, STOCH>(*r.hs, c);
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
-    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
+    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
     const size_t smem = 128 + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
@@ -174,7 +212,7 @@ template <class Real, class Io>
 static int sc_launch_generic(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
-    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset};
+    ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
     const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
     const bool exact = r.mode == SCG_MODE_EXACT_F64;

@@ -17,13 +17,19 @@
 
 namespace scg {
 
+#ifndef SCG_FIXED_RING
+#define SCG_FIXED_RING 1        // mixed mode, constant lead time: in-transit material as 32-bit fixed point (RingFixed)
+#endif
+
 // L = avg_leadtime (constant lead time when !STOCH; number of obs buckets), ML = max_leadtime = ring depth.
 template <class Real, int S, int F, int W, int R, int P, int L, int ML, bool STOCH>
 struct LayeredConsts {
     static constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
     Real cap[NP], hold[NP], stock0[NP], max_ship[NP], init_slot[NP * ML];
+    Real q_scale[NP], q_inv[NP];                         // fixed-point ring (RingFixed): slot = amount * q_scale, a power of two
     unsigned long long lt_thr[ML];                       // stochastic lead times: lt = 1 + #{j < ML-1 : word >= lt_thr[j]}
-    float obs_stock[NP], obs_mid[NP], obs_last[NP];      // 1/cap, 1/max_ship, 1/(max_ship*(maxL-avgL+1)) (non-exact obs path)
+    float obs_stock[NP], obs_mid[NP], obs_last[NP];      // 1/cap, 1/max_ship, 1/(max_ship*(maxL-avgL+1)) (non-exact obs path;
+                                                         // the last two times q_inv where the ring is fixed-point)
     Real sup_cap[S * P], sup_cost[S * P];
     Real proc_cap[F], ratio[F * P], inv_ratio[F * P], proc_cost[F * P];
     Real ecap[E], ecost[E * P];
@@ -208,8 +214,14 @@ template <class Real, int NP, int L, bool STOCH>
 struct RingRegs {
     static constexpr bool kTwoPhase = true;
     static constexpr bool kExactObs = false;
+    static constexpr bool kFixed = false;
     Real stock[NP];
     Real slot[NP * L];
+    __device__ __forceinline__ RingRegs(const Real*, const Real*) {}
+    __device__ __forceinline__ void commit() {}
+    __device__ __forceinline__ void load_slot(int i, Real v) { slot[i] = v; }
+    __device__ __forceinline__ Real store_slot(int i) const { return slot[i]; }
+    __device__ __forceinline__ float obs_slot(int i) const { return (float)slot[i]; }
     __device__ __forceinline__ Real get_stock(int np) const { return stock[np]; }
     __device__ __forceinline__ void set_stock(int np, Real v) { stock[np] = v; }
     __device__ __forceinline__ Real slot_at(int np, int k) const { return slot[np * L + k]; }
@@ -228,6 +240,56 @@ struct RingRegs {
         }
     }
 };
+
+// Fixed-point lead-time ring for the fp64-state / fp32-I/O kernels with a constant lead time (SCG_MODE_MIXED).
+//
+// Stocks integrate over the whole episode and stay fp64.  In-transit material does not integrate: a slot is written in
+// one period (the sum of what its <= n_src sources push) and consumed L periods later, so it only has to be held to a
+// fixed ABSOLUTE resolution.  Each slot is a 32-bit unsigned integer in units of q_inv[np] = 2^-k, k chosen on the host
+// from the largest amount that can be in flight to that (node, product) (sc_fill_consts: q = bound * 2^-31, e.g.
+// 2.8e-6 for an ntom retailer -- fp32 would resolve 3e-5 there).  That halves the registers of the ring (48 instead of
+// 96 for ntom -> the kernel fits 10-11 warps per SM instead of 8), the per-period shift becomes one move per slot, and
+// the observation reads the slot with an ALU int->float conversion instead of an fp64->fp32 one.  This period's pushes
+// are accumulated in fp64 (`acc`, live only between the first and the last source of a destination) and rounded ONCE
+// in commit(); conversions saturate, so an out-of-contract supply action far outside [-1, 1] clips at 8x capacity.
+template <int NP, int L>
+struct RingFixed {
+    static constexpr bool kTwoPhase = true;
+    static constexpr bool kExactObs = false;
+    static constexpr bool kFixed = true;
+    double stock[NP];
+    unsigned slot[NP * L];
+    double acc[NP];
+    bool has[NP];                      // compile-time after unrolling: the first push of a period is an assignment
+    const double* q_scale; const double* q_inv;
+    __device__ __forceinline__ RingFixed(const double* qs, const double* qi) : q_scale(qs), q_inv(qi) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { acc[i] = 0.0; has[i] = false; }
+    }
+    __device__ __forceinline__ double get_stock(int np) const { return stock[np]; }
+    __device__ __forceinline__ void set_stock(int np, double v) { stock[np] = v; }
+    __device__ __forceinline__ double arrive(int np, int) {
+        const double a = (double)slot[np * L] * q_inv[np];
+#pragma unroll
+        for (int k = 0; k + 1 < L; ++k) slot[np * L + k] = slot[np * L + k + 1];
+        has[np] = false;
+        return a;
+    }
+    __device__ __forceinline__ void push(int np, int, int, double amount) {
+        acc[np] = has[np] ? acc[np] + amount : amount;
+        has[np] = true;
+    }
+    __device__ __forceinline__ void commit() {
+#pragma unroll
+        for (int np = 0; np < NP; ++np) slot[np * L + L - 1] = has[np] ? __double2uint_rn(acc[np] * q_scale[np]) : 0u;
+    }
+    __device__ __forceinline__ void load_slot(int i, double v) { slot[i] = __double2uint_rn(v * q_scale[i / L]); }
+    __device__ __forceinline__ double store_slot(int i) const { return (double)slot[i] * q_inv[i / L]; }
+    __device__ __forceinline__ float obs_slot(int i) const { return (float)slot[i]; }     // host folds q_inv into obs_mid / obs_last
+};
+
+template <bool FIXED, class Real, int NP, int L, bool STOCH> struct PipeChoice { using type = RingRegs<Real, NP, L, STOCH>; };
+template <int NP, int L> struct PipeChoice<true, double, NP, L, false> { using type = RingFixed<NP, L>; };
 
 // Reads one env's row of LEN elements out of the warp tile, 16/8/4 bytes at a time.  All
 // indices are compile-time constants after unrolling, so the chunk cache folds away.
@@ -357,7 +419,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) 
 // the fused rollout kernel
 // ---------------------------------------------------------------------------------
 template <class Real, class Io, int S, int F, int W, int R, int P, int L, int ML, bool STOCH, bool RANDOM_ACT, int THREADS, int MINB>
+#ifdef SCG_MAXNREG
+__global__ void __maxnreg__(SCG_MAXNREG)
+#else
 __global__ void __launch_bounds__(THREADS, MINB)
+#endif
 sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH> c, ScDevSpec<Real> sp, ScState<Real> st,
                    ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
                    Io* __restrict__ reward, unsigned char* __restrict__ done) {
@@ -388,7 +454,10 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
 
-    RingRegs<Real, NP, ML, STOCH> pp;
+    // fp64 state with fp32 I/O and a constant lead time: in-transit material as 32-bit fixed point (RingFixed)
+    constexpr bool kFixed = (SCG_FIXED_RING != 0) && sizeof(Real) == 8 && sizeof(Io) == 4 && !STOCH;
+    using Pp = typename PipeChoice<kFixed, Real, NP, ML, STOCH>::type;
+    Pp pp(c.q_scale, c.q_inv);
     RegDemand<RP> dm;
     int t = 0; unsigned episode = 0; double ep_ret = 0.0;
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
@@ -420,7 +489,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 #pragma unroll
         for (int i = 0; i < NP; ++i) pp.stock[i] = st.stock[(long long)i * n + env];
 #pragma unroll
-        for (int i = 0; i < NP * ML; ++i) pp.slot[i] = st.slot[(long long)i * n + env];
+        for (int i = 0; i < NP * ML; ++i) pp.load_slot(i, st.slot[(long long)i * n + env]);
         fetch_next_demand(t);
     }
 
@@ -448,6 +517,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
             if constexpr (!STOCH) {
                 ConstLeadtime<L> lr;
                 cost = sc_step_nodes<Real>(tp, pp, t, ar, lr, dm);
+                pp.commit();
             } else {
                 // this period's K lead times: injected table, or 1 + Poisson(avg-1) clipped to ML by integer
                 // thresholds on one Philox word each (same words and thresholds as the generic kernel)
@@ -455,7 +525,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                 lr.clear();
                 if (in.inj_leadtimes != nullptr) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) lr.set(k, in.inj_leadtimes[((long long)(t - 1) * K + k) * n + env]);
+                    for (int k = 0; k < K; ++k) lr.set(k, checked_leadtime(in.inj_leadtimes[((long long)(t - 1) * K + k) * n + env], ML, in.err));
                 } else {
 #pragma unroll
                     for (int b = 0; b < (K + 3) / 4; ++b) {
@@ -485,7 +555,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 #pragma unroll
                     for (int i = 0; i < NP; ++i) pp.stock[i] = c.stock0[i];
 #pragma unroll
-                    for (int i = 0; i < NP * ML; ++i) pp.slot[i] = c.init_slot[i];
+                    for (int i = 0; i < NP * ML; ++i) pp.load_slot(i, c.init_slot[i]);
                 }
             }
         }
@@ -525,14 +595,18 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                         const int np = nn * P + p;
 #pragma unroll
                         for (int k = 0; k + 1 < L; ++k) {
-                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(pp.slot[np * ML + k] / c.max_ship[np]));
-                            else ow.put(o++, unit((float)pp.slot[np * ML + k], c.obs_mid[np]));
+                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(c.max_ship[np] > (Real)0 ? pp.slot[np * ML + k] / c.max_ship[np] : (Real)0));
+                            else ow.put(o++, unit(pp.obs_slot(np * ML + k), c.obs_mid[np]));
                         }
-                        Real rest = (Real)0;                       // everything arriving at t+L or later
+                        if constexpr (kFixed) {
+                            ow.put(o++, unit(pp.obs_slot(np * ML + L - 1), c.obs_last[np]));     // ML == L: one slot
+                        } else {
+                            Real rest = (Real)0;                   // everything arriving at t+L or later
 #pragma unroll
-                        for (int k = L - 1; k < ML; ++k) rest += pp.slot[np * ML + k];
-                        if constexpr (kExact) ow.put(o++, obs_norm<Real>(rest / (c.max_ship[np] * (Real)(ML - (L - 1)))));
-                        else ow.put(o++, unit((float)rest, c.obs_last[np]));
+                            for (int k = L - 1; k < ML; ++k) rest += pp.slot[np * ML + k];
+                            if constexpr (kExact) ow.put(o++, obs_norm<Real>(c.max_ship[np] > (Real)0 ? rest / (c.max_ship[np] * (Real)(ML - (L - 1))) : (Real)0));
+                            else ow.put(o++, unit((float)rest, c.obs_last[np]));
+                        }
                     }
                 }
                 if constexpr (kExact) ow.put(o++, obs_norm<Real>((Real)(c.T - t) / (Real)c.T));
@@ -558,7 +632,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 #pragma unroll
         for (int i = 0; i < NP; ++i) st.stock[(long long)i * n + env] = pp.stock[i];
 #pragma unroll
-        for (int i = 0; i < NP * ML; ++i) st.slot[(long long)i * n + env] = pp.slot[i];
+        for (int i = 0; i < NP * ML; ++i) st.slot[(long long)i * n + env] = pp.store_slot(i);
     }
     rs.flush(st.stats);
 }

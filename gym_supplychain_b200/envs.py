@@ -178,8 +178,16 @@ class _ScgEnvBase(object):
         return blob
 
     def set_state(self, blob):
-        assert blob.numel() == self.scg_info.state_bytes and blob.is_cuda
+        torch = _torch()
+        if (not torch.is_tensor(blob) or not blob.is_cuda or blob.dtype != torch.uint8
+                or blob.numel() != self.scg_info.state_bytes):
+            raise ValueError("set_state: need a CUDA uint8 tensor of %d bytes (get_state())" % self.scg_info.state_bytes)
         _lib.check(self._lib.scg_set_state(self._h, self._ptr(blob.contiguous()), self._stream()))
+
+    def check(self, clear=True):
+        """Synchronise and raise ScgError if a kernel flagged a device-side check (scg_status): an injected lead time /
+        delay out of range (clamped, never out of bounds) or an in-transit queue overflow."""
+        _lib.check(self._lib.scg_status(self._h, 1 if clear else 0))
 
     def launch_count(self):
         return int(self._lib.scg_launch_count(self._h))
@@ -261,17 +269,29 @@ class SupplyChainEnv(_ScgEnvBase):
         torch = _torch()
         T, R, P = self.flat.T, self.flat.n_retailers, self.flat.P
 
-        def prep(x, shape):
+        def prep(x, shape, what):
             if x is None:
                 return None
             x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(torch.int32)
+            if tuple(x.shape) not in (tuple(shape), (self.num_envs,) + tuple(shape)):
+                raise ValueError("inject: %s must have shape %s or %s, got %s"
+                                 % (what, tuple(shape), (self.num_envs,) + tuple(shape), tuple(x.shape)))
             if x.dim() == len(shape):
                 x = x.unsqueeze(0).expand((self.num_envs,) + tuple(shape))
-            assert tuple(x.shape) == (self.num_envs,) + tuple(shape), (tuple(x.shape), shape)
-            x = x.reshape(self.num_envs, shape[0], -1).permute(1, 2, 0).contiguous()   # [rows][cols][env]
-            return x.to(self.device)
-        d = prep(demand, (T + 1, R, P))
-        lt = prep(leadtimes, (T, self.flat.n_leadtimes)) if self.flat.stochastic_leadtimes else None
+            return x
+        d = prep(demand, (T + 1, R, P), "demand")
+        lt = prep(leadtimes, (T, self.flat.n_leadtimes), "leadtimes") if self.flat.stochastic_leadtimes else None
+        if lt is not None and lt.numel() > 0:
+            # the reference draws clip(1 + Poisson(avg - 1), 1, max_leadtime) (supplychain_env.py:670-672); the in-transit
+            # ring / queues are sized for exactly that range (the kernels clamp and flag anything else, scg_status)
+            lo, hi = int(lt.min()), int(lt.max())
+            if lo < 1 or hi > self.flat.max_leadtime:
+                raise ValueError("inject: lead times must lie in [1, max_leadtime=%d], got [%d, %d]"
+                                 % (self.flat.max_leadtime, lo, hi))
+
+        def lay(x):            # [env][rows][cols...] -> device [rows][cols][env]
+            return None if x is None else x.reshape(self.num_envs, x.shape[1], -1).permute(1, 2, 0).contiguous().to(self.device)
+        d, lt = lay(d), lay(lt)
         self._inj = (d, lt)                                     # keep the tensors alive
         torch.cuda.current_stream(self.device).synchronize()    # the *_host calls run on the handle's own stream
         _lib.check(self._lib.scg_inject(self._h, self._ptr(d), self._ptr(lt)))
@@ -427,12 +447,14 @@ class _BeerGameBase(_ScgEnvBase):
             x = torch.as_tensor(np.asarray(x)).to(torch.int32)
             if x.dim() == 1:
                 x = x.unsqueeze(0).expand(self.num_envs, -1)
-            assert tuple(x.shape) == (self.num_envs, self.max_weeks)
+            if tuple(x.shape) != (self.num_envs, self.max_weeks):
+                raise ValueError("inject: need shape (%d,) or (%d, %d), got %s"
+                                 % (self.max_weeks, self.num_envs, self.max_weeks, tuple(x.shape)))
             return x.t().contiguous().to(self.device)
         d, dl = prep(demand), prep(delays)
-        if dl is not None and int(dl.max()) > self.scg_info.ring_depth:
-            raise ValueError("injected delay %d exceeds the in-transit ring depth %d of this env"
-                             % (int(dl.max()), self.scg_info.ring_depth))
+        if dl is not None and (int(dl.max()) > self.scg_info.ring_depth or int(dl.min()) < 0):
+            raise ValueError("injected delays must lie in [0, %d] (the in-transit ring depth of this env), got [%d, %d]"
+                             % (self.scg_info.ring_depth, int(dl.min()), int(dl.max())))
         self._inj = (d, dl)
         torch.cuda.current_stream(self.device).synchronize()    # the *_host calls run on the handle's own stream
         _lib.check(self._lib.scg_inject(self._h, self._ptr(d), self._ptr(dl)))

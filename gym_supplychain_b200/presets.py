@@ -9,8 +9,8 @@ ready for `FlatSpec(nodes_info, **env_kwargs)`:
   multi_product (+variants)  SupplyChainMultiProduct*           supplychain_multiproduct_env.py:56-273
   main_demo_chain .......... the 2-2-2-2 chain of supplychain_env.py:842-868 (default for supplychain-v0)
 
-tests/test_presets.py pins every one of them against the nodes_info the reference classes build
-(captured into tests/golden/*.npz).
+tests/test_host_cpu.py (test_presets_reproduce_reference_nodes_info) pins every one of them against the
+nodes_info the reference classes build (captured into tests/golden/*.npz).
 """
 
 _ENV_KEYS = ("num_products", "unmet_demand_cost", "exceeded_stock_capacity_cost", "exceeded_process_capacity_cost",

@@ -177,7 +177,8 @@ SCG_API int  scg_sc_precompile(const ScgSupplyChainSpec* spec, int32_t mode, int
 SCG_API void scg_destroy(ScgHandle h);
 SCG_API int  scg_info(ScgHandle h, ScgInfo* out);
 
-/* New Philox key; the episode counters restart (SupplyChainEnv.seed, :811-813). */
+/* New Philox key; the episode counters restart (SupplyChainEnv.seed, :811-813).  Host-synchronous: the device is
+ * synchronised before and after, so work already enqueued on any stream keeps the old key and nothing new overtakes. */
 SCG_API int  scg_seed(ScgHandle h, uint64_t seed);
 
 /* Replace the on-device generators by caller-provided tables for the NEXT episodes
@@ -187,6 +188,14 @@ SCG_API int  scg_seed(ScgHandle h, uint64_t seed);
  * Either may be NULL (= keep generating that input).  The tables are NOT copied: they
  * must stay alive until replaced or the handle is destroyed. */
 SCG_API int  scg_inject(ScgHandle h, const int32_t* demand, const int32_t* leadtimes);
+
+/* Device-side checks.  Kernels validate what they cannot trust: an injected lead time outside [1, max_leadtime]
+ * (the reference draws clip(1 + Poisson, 1, max), supplychain_env.py:670-672) or an injected beer-game delay outside
+ * [0, ring_depth] is CLAMPED (never an out-of-bounds access) and an in-transit queue that overflows its capacity drops
+ * the entry; either raises a sticky bit on the handle.  scg_status synchronises the device and returns SCG_OK or
+ * SCG_ESTATE (scg_last_error names the check); clear != 0 resets the bits.  The *_host calls, being synchronous,
+ * report the same condition through their own return code. */
+SCG_API int  scg_status(ScgHandle h, int32_t clear);
 
 /* reset(): `mask` NULL = every env, else uint8[n_envs] (non-zero = reset).  `obs` may be NULL. */
 SCG_API int  scg_reset(ScgHandle h, const uint8_t* mask, void* obs, void* stream);
@@ -201,7 +210,9 @@ SCG_API int  scg_rollout(ScgHandle h, int32_t T, const void* actions, void* obs,
                  void* stream);
 
 /* Same calls with HOST buffers (pageable or pinned): the library stages them through its own
- * device buffers (H2D, kernel, D2H) and returns when the results are in the host buffers. */
+ * device buffers (H2D, kernel, D2H) and returns when the results are in the host buffers.  They run on the library's
+ * own streams, ordered BEHIND every earlier device-pointer call on this handle (scg_reset / scg_step / scg_rollout /
+ * scg_set_state record an event on the caller's stream that the host calls wait for). */
 SCG_API int  scg_reset_host(ScgHandle h, const uint8_t* mask, void* obs);
 SCG_API int  scg_step_host(ScgHandle h, const void* actions, void* obs, void* reward, uint8_t* done);
 SCG_API int  scg_rollout_host(ScgHandle h, int32_t T, const void* actions, void* obs, void* reward, uint8_t* done);

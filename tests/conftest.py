@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` need a CUDA device: skip them (instead of failing with ScgError) on a CPU-only machine."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run with -m gpu on the GPU box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def pytest_sessionstart(session):
     """The tests exercise the built C-ABI library; build it (nvcc cross-compiles without a GPU) if the tree is fresh.
     The product itself never builds implicitly: without libscg.so it fails loudly."""

@@ -21,7 +21,3 @@ def load(kind, name):
     meta = json.loads(str(z["meta"]))
     return meta, z
 
-
-def tuplify_env_kwargs(kw):
-    """JSON turned tuples into lists; SupplyChainEnv-style kwargs accept either."""
-    return dict(kw)
