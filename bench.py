@@ -783,19 +783,25 @@ def c4s_shape(world):
     return n_local, T_launch, 128 // T_launch
 
 
-def cpu_reference_block(cfg, cores, budget_eps):
-    """Bounded sample of the reference for config `cfg` on all host cores (rank 0, N=1)."""
+def cpu_reference_block(cfg, cores, budget_s):
+    """Bounded sample of the reference for config `cfg` on all host cores (rank 0, N=1): after a warm-up map (imports, first
+    reset) each env family runs whole episodes, map after map, until `budget_s` seconds of wall time are spent on it."""
+    eps_per_map = {"ntom": 2, "linear": 12, "2perstage": 6, "supplychain-v0": 1, "beergame-v0": 100, "beergame-v2-stochastic": 40}
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         per = []
         for case, T, wgt in REF_SAMPLE[cfg]:
             cpu_rate(pool, cores, case, 1, min(T, 16))
-            r, wall = cpu_rate(pool, cores, case, budget_eps[case], T)
-            per.append((r, wgt, case, wall))
-    return {"value": mixed_rate([(r, w) for r, w, _, _ in per]), "unit": "env-steps/s", "cores": cores, "cpu": cpu_model(),
+            steps, t0, maps = 0, time.perf_counter(), 0
+            while time.perf_counter() - t0 < budget_s / len(REF_SAMPLE[cfg]):
+                res = pool.map(_ref_worker, [(case, 1000 * maps + i, eps_per_map[case], T) for i in range(cores)])
+                steps += sum(r[0] for r in res); maps += 1
+            wall = time.perf_counter() - t0
+            per.append((steps / wall, wgt, case, wall, maps * eps_per_map[case], T))
+    return {"value": mixed_rate([(r, w) for r, w, _, _, _, _ in per]), "unit": "env-steps/s", "cores": cores, "cpu": cpu_model(),
             "kind": "reference",
-            "sample": "; ".join("%s: %d workers x %d episodes x %d periods in %.1f s (%.3g env-steps/s)"
-                                % (c, cores, budget_eps[c], T, wall, r) for (r, _, c, wall), (_, T, _) in zip(per, REF_SAMPLE[cfg]))}
+            "sample": "; ".join("%s: %d workers x %d episodes x %d periods (reset() included) in %.1f s = %.3g env-steps/s"
+                                % (c, cores, eps, T, wall, r) for r, _, c, wall, eps, T in per)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -915,16 +921,13 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload, the reference itself, on the host cores ----
     cpu = None
     if want_cpu:
-        eps = {"ntom": args.cpu_eps, "linear": 6 * args.cpu_eps, "2perstage": 3 * args.cpu_eps, "supplychain-v0": max(1, args.cpu_eps // 3),
-               "beergame-v0": 100 * args.cpu_eps, "beergame-v2-stochastic": 40 * args.cpu_eps}
         if reference_available():
-            cpu = cpu_reference_block(cfg, cores, eps)
+            cpu = cpu_reference_block(cfg, cores, args.cpu_seconds)
             if not args.no_other:
-                quick = {k: max(1, v // 4) for k, v in eps.items()}
                 for oc in ("c2", "c3", "c5"):
                     if oc in other and isinstance(other[oc], dict) and "error" not in other[oc]:
                         try:
-                            other[oc]["cpu_baseline"] = cpu_reference_block(oc, cores, quick)
+                            other[oc]["cpu_baseline"] = cpu_reference_block(oc, cores, max(2.0, args.cpu_seconds / 4))
                         except Exception as e:  # noqa: BLE001
                             other[oc]["cpu_baseline"] = {"unavailable": str(e)[:200]}
         else:
@@ -936,14 +939,14 @@ def run_ours(args):
                 try:
                     pool.map(_port_worker, [(i, 1, 16) for i in range(cores)])
                     t0 = time.perf_counter()
-                    res = pool.map(_port_worker, [(i, max(1, args.cpu_eps // 2), 128) for i in range(cores)])
+                    res = pool.map(_port_worker, [(i, 4, 128) for i in range(cores)])
                     cpu["port"] = {"value": sum(r[0] for r in res) / (time.perf_counter() - t0), "unit": "env-steps/s", "cores": cores,
                                    "what": "oracle/sc_oracle.py (Python restatement of the reference loop)"}
                     from oracle import c_oracle
                     c_oracle.build()
                     pool.map(_c_port_worker, [(i, 2, 128) for i in range(cores)])
                     t0 = time.perf_counter()
-                    res = pool.map(_c_port_worker, [(100 + i, 400 * args.cpu_eps, 128) for i in range(cores)])
+                    res = pool.map(_c_port_worker, [(100 + i, 1500, 128) for i in range(cores)])
                     cpu["c_port"] = {"value": sum(r[0] for r in res) / (time.perf_counter() - t0), "unit": "env-steps/s", "cores": cores,
                                      "what": "oracle/sc_oracle.c (plain C restatement, gcc -O2), one process per core"}
                 except Exception as e:  # noqa: BLE001
@@ -982,7 +985,7 @@ def main():
     ap.add_argument("--rollout-T", type=int, default=128)
     ap.add_argument("--e2e-T", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-eps", type=int, default=4, help="episodes (reset + 128 periods) per host core in the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall-time budget of the CPU (reference) baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE.json configs (other_configs block)")
     ap.add_argument("--seed", type=int, default=0)

@@ -343,6 +343,7 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     I.n_envs = opt->n_envs; I.family = 0; I.mode = opt->mode; I.n_actions = h->hs.A; I.n_obs = h->hs.O;
     I.n_demands = h->hs.RP; I.n_leadtimes = h->hs.K; I.total_time_steps = h->hs.T; I.elem_size = (is_f64(opt->mode) && opt->mode != SCG_MODE_MIXED) ? 8 : 4;
     I.ring_depth = h->hs.ring; I.heap_capacity = h->hs.heapcap; I.kernel_variant = h->variant; I.state_bytes = (int64_t)h->state_bytes;
+    if (h->variant == SC_VARIANT_JIT && sc_jit_split_lanes(h->hs, opt->mode) > 0) I.kernel_variant = SC_VARIANT_JIT_SPLIT;
     I.info_values = (opt->flags & SCG_FLAG_BUILD_INFO) ? 16 * h->hs.P : 0;
     rc = dispatch(h, SC_OP_RESET, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc == SCG_OK) { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { set_error("initial reset failed: %s", cudaGetErrorString(e)); rc = SCG_ECUDA; } }

@@ -23,9 +23,14 @@ namespace scg {
 #endif
 constexpr int BG_PF = SCG_BG_PF;
 
-template <int LMAX, int RMAX, bool STATIC>
-__global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand,
-                                                 const int32_t* __restrict__ inj_delays, RngKey key, long long first_env,
+// VER: -1 = the game version is read at run time, 0 / 2 = known (beergame-v0 / -v2).
+// INP:  0 = where demand / delay come from is decided at run time (injected tables, Philox, the spec's tables, any mix),
+//       1 = both from the spec's per-week tables (the reference's default configuration), 2 = both from Philox
+//       (customer_demand=(lo,hi), shipment_delays=(lo,hi): beergame2_env.py:86-92).  The specialisations drop ~30 uniform
+//       tests and branches per week from a kernel that moves only 37 bytes per env-week.
+template <int LMAX, int RMAX, bool STATIC, int VER, int INP>
+__global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand_,
+                                                 const int32_t* __restrict__ inj_delays_, RngKey key, long long first_env,
                                                  int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
                                                  int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
                                                  int32_t* __restrict__ reward, unsigned char* __restrict__ done, int* err) {
@@ -33,6 +38,9 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
     const long long n = st.n;
     const int L = STATIC ? LMAX : sp.L;
     const int RING = STATIC ? RMAX : sp.ring;
+    const bool v2 = VER < 0 ? sp.version == 2 : VER == 2;
+    const int32_t* inj_demand = INP == 0 ? inj_demand_ : nullptr;
+    const int32_t* inj_delays = INP == 0 ? inj_delays_ : nullptr;
     // the per-week demand / delay tables are shared by every env: stage them in shared memory once per block
     // (a dependent global load per week, even an L1 hit, was the dominant stall of the first version)
     extern __shared__ int s_tab[];
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                 for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] = st.transit[((long long)k * L + i) * n + env];
             }
         }
-        const int off = sp.version == 2 ? sp.max_stock : 0;            // beergame2_env.py:111-112
+        const int off = v2 ? sp.max_stock : 0;                           // beergame2_env.py:111-112
         auto write_obs = [&](long long io) {
             if (obs == nullptr) return;
             if (STATIC && LMAX == 4) {
@@ -85,8 +93,8 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
         const int4* act4 = reinterpret_cast<const int4*>(actions);
 
         // one week of one env; `a_now` is the (pre-loaded) action row of the 4-level fast path
+        long long io = env;                                            // running index of (week s, this env) in the [T, n] outputs
         auto week_step = [&](int s, int4 a_now) {
-            const long long io = (long long)s * n + env;
             if (week >= sp.T) {                                        // finished, not auto-reset: frozen
                 write_obs(io); reward[io] = 0; done[io] = 1;
                 return;
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                 Philox4 b1 = rng_block(key, genv, episode, (unsigned)(week + 1), STREAM_ACTION, 1);
 #pragma unroll
                 for (int i = 0; i < LMAX; ++i)
-                    if (i < L) act[i] = sp.version == 2 ? uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), 0, (unsigned)sp.max_order)
+                    if (i < L) act[i] = v2 ? uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), 0, (unsigned)sp.max_order)
                                                         : uniform_int(pick_word(i < 4 ? b0 : b1, i & 3), -2, 7);
             } else if (STATIC && LMAX == 4) {
                 act[0] = a_now.x; act[1] = a_now.y; act[2] = a_now.z; act[3] = a_now.w;
@@ -116,7 +124,8 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
             // customer demand and this week's delay; when both are stochastic they share one Philox block
             // keyed (env, episode, week): word x -> demand, word y -> delay (randint(lo, hi): hi exclusive)
             int dem, delay;
-            const bool rnd_dem = !inj_demand && sp.dem_hi > sp.dem_lo, rnd_del = !inj_delays && sp.del_hi > sp.del_lo;
+            const bool rnd_dem = INP == 0 ? (!inj_demand && sp.dem_hi > sp.dem_lo) : INP == 2;
+            const bool rnd_del = INP == 0 ? (!inj_delays && sp.del_hi > sp.del_lo) : INP == 2;
             Philox4 wk = Philox4{0, 0, 0, 0};
             if (rnd_dem || rnd_del) wk = rng_block(key, genv, episode, (unsigned)week, STREAM_BG_DEMAND, 0);
             if (inj_demand) dem = inj_demand[(long long)(week - 1) * n + env];
@@ -159,13 +168,13 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
             }
             // 5. place orders (beergame_env.py:121 / beergame2_env.py:168)
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) if (i < L) placed[i] = sp.version == 2 ? act[i] : incoming[i] + act[i];
+            for (int i = 0; i < LMAX; ++i) if (i < L) placed[i] = v2 ? act[i] : incoming[i] + act[i];
             // 6. reward (:130 / beergame2_env.py:177-180)
             int r = 0;
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) if (i < L) {
                 r -= sp.inv_cost * inv[i] + sp.backlog_cost * back[i];
-                if (sp.version == 2) r -= sp.penalty * (max(inv[i] - sp.max_stock, 0) + max(back[i] - sp.max_stock, 0));
+                if (v2) r -= sp.penalty * (max(inv[i] - sp.max_stock, 0) + max(back[i] - sp.max_stock, 0));
             }
             ep_ret += (double)r;
             const bool fin = (week == sp.T);
@@ -195,12 +204,12 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                 }
 #pragma unroll
                 for (int u = 0; u < BG_PF; ++u)
-                    if (g + u < n_steps) week_step(g + u, cur[u]);
+                    if (g + u < n_steps) { week_step(g + u, cur[u]); io += n; }
 #pragma unroll
                 for (int u = 0; u < BG_PF; ++u) cur[u] = nxt[u];
             }
         } else {
-            for (int s = 0; s < n_steps; ++s) week_step(s, make_int4(0, 0, 0, 0));
+            for (int s = 0; s < n_steps; ++s) { week_step(s, make_int4(0, 0, 0, 0)); io += n; }
         }
         st.week[env] = week; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
 #pragma unroll
@@ -222,13 +231,24 @@ int bg_run(const BgRun& r) {
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
     const size_t smem = (size_t)2 * r.sp.T * sizeof(int);
     if (smem > 48 * 1024) { set_error("beer game: more than 6144 weeks per episode not supported"); return SCG_EINVAL; }
-#define SCG_BG_LAUNCH(LM, RM, ST)                                                                              \
-    bg_kernel<LM, RM, ST><<<blocks, threads, smem, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,      \
-                                                            r.first_env, r.auto_reset, n_steps, r.reset_mask,   \
-                                                            do_reset, r.actions, r.obs, r.reward, r.done, r.err)
-    if (r.sp.L == 4 && r.sp.ring == 2) SCG_BG_LAUNCH(4, 2, true);
-    else if (r.sp.L == 4 && r.sp.ring == 4) SCG_BG_LAUNCH(4, 4, true);
-    else SCG_BG_LAUNCH(8, 8, false);
+#define SCG_BG_LAUNCH(LM, RM, ST, VER, INP)                                                                              \
+    bg_kernel<LM, RM, ST, VER, INP><<<blocks, threads, smem, r.stream>>>(r.sp, r.st, r.inj_demand, r.inj_delays, r.key,       \
+                                                                      r.first_env, r.auto_reset, n_steps, r.reset_mask,    \
+                                                                      do_reset, r.actions, r.obs, r.reward, r.done, r.err)
+    // where this launch's demand / delays come from: 1 = the spec's tables, 2 = Philox for both, 0 = anything else
+    const bool rnd_dem = r.sp.dem_hi > r.sp.dem_lo, rnd_del = r.sp.del_hi > r.sp.del_lo;
+    const int inp = (r.inj_demand || r.inj_delays) ? 0 : ((!rnd_dem && !rnd_del) ? 1 : ((rnd_dem && rnd_del) ? 2 : 0));
+#define SCG_BG_PICK(RM)                                                                                                     \
+    do {                                                                                                                    \
+        if (inp == 1 && r.sp.version == 2) SCG_BG_LAUNCH(4, RM, true, 2, 1);                                                \
+        else if (inp == 1) SCG_BG_LAUNCH(4, RM, true, 0, 1);                                                                \
+        else if (inp == 2 && r.sp.version == 2) SCG_BG_LAUNCH(4, RM, true, 2, 2);                                           \
+        else SCG_BG_LAUNCH(4, RM, true, -1, 0);                                                                             \
+    } while (0)
+    if (r.sp.L == 4 && r.sp.ring == 2) SCG_BG_PICK(2);
+    else if (r.sp.L == 4 && r.sp.ring == 4) SCG_BG_PICK(4);
+    else SCG_BG_LAUNCH(8, 8, false, -1, 0);
+#undef SCG_BG_PICK
 #undef SCG_BG_LAUNCH
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;

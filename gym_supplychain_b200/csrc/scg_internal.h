@@ -76,10 +76,12 @@ int sc_build_devspec_f64(const ScHostSpec& hs, void** blob_out, void* devspec_ou
 // Run-time instantiation of the layered kernel for shapes without a pre-built one (scg_jit.cu)
 struct ScJit;
 bool sc_jit_match(const ScHostSpec& hs, int mode);      // layered chain + NVRTC and the driver entry points are available
+int sc_jit_split_lanes(const ScHostSpec& hs, int mode);  // > 0: the chain gets the node-parallel kernel with that many lanes per env
 int sc_jit_run(ScJit** cache, const ScRun& r);          // SCG_OK, or an error after which the caller uses the generic kernel
 void sc_jit_free(ScJit* cache);
 int sc_jit_precompile(const ScHostSpec& hs, int mode, bool random_act);   // NVRTC only, no GPU needed
 constexpr int SC_VARIANT_JIT = 100;
+constexpr int SC_VARIANT_JIT_SPLIT = 101;     // reported in ScgInfo.kernel_variant only (dispatch uses SC_VARIANT_JIT)
 
 // Beer game
 struct BgHostSpec {

@@ -275,6 +275,7 @@ struct JitKernel {
 struct ScJit {
     bool failed = false;
     int S = 0, F = 0, W = 0, R = 0, ML = 0, threads = 0, minb = 0;
+    int split_g = 0;           // > 0: the node-parallel kernel (scg_sc_split.cuh) with that many lanes per env
     size_t smem = 0;
     Packed consts;
     JitKernel k[2];            // [random actions ?]
@@ -308,6 +309,11 @@ bool sc_jit_match(const ScHostSpec& hs, int mode) {
     return jit_plan(probe, hs, mode) && load_backends();
 }
 
+int sc_jit_split_lanes(const ScHostSpec& hs, int mode) {
+    ScJit probe;
+    return jit_plan(probe, hs, mode) ? probe.split_g : 0;
+}
+
 void sc_jit_free(ScJit* j) {
     if (!j) return;
     for (auto& k : j->k) if (k.mod && g_drv.ok) g_drv.ModuleUnload(k.mod);
@@ -321,13 +327,19 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     const char* real = mode == SCG_MODE_FAST_F32 ? "float" : "double";
     const char* io = mode == SCG_MODE_FAST_F64 ? "double" : "float";
     char name[512];
-    snprintf(name, sizeof(name), "scg::sc_layered_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %s, %d, %d>", real, io, j.S, j.F, j.W,
-             j.R, hs.P, hs.avgL, j.ML, hs.stochL ? "true" : "false", random_act ? "true" : "false", j.threads, j.minb);
     std::ostringstream src;
-    src << "#include \"scg_sc_static.cuh\"\nnamespace scg {\nusing JitC = LayeredConsts<" << real << ", " << j.S << ", " << j.F << ", " << j.W
-        << ", " << j.R << ", " << hs.P << ", " << hs.avgL << ", " << j.ML << ", " << (hs.stochL ? "true" : "false") << ">;\n"
-        << "static_assert(sizeof(JitC) == " << j.consts.b.size() << ", \"LayeredConsts layout: host packer out of date\");\n";
-    src << "}\n";
+    if (j.split_g > 0) {
+        snprintf(name, sizeof(name), "scg::sc_split_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %d, %d>", real, io, j.S, j.F, j.W, j.R,
+                 hs.P, hs.avgL, j.split_g, random_act ? "true" : "false", j.threads, j.minb);
+        src << "#include \"scg_sc_split.cuh\"\n";
+    } else {
+        snprintf(name, sizeof(name), "scg::sc_layered_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %s, %d, %d>", real, io, j.S, j.F, j.W,
+                 j.R, hs.P, hs.avgL, j.ML, hs.stochL ? "true" : "false", random_act ? "true" : "false", j.threads, j.minb);
+        src << "#include \"scg_sc_static.cuh\"\nnamespace scg {\nusing JitC = LayeredConsts<" << real << ", " << j.S << ", " << j.F << ", " << j.W
+            << ", " << j.R << ", " << hs.P << ", " << hs.avgL << ", " << j.ML << ", " << (hs.stochL ? "true" : "false") << ">;\n"
+            << "static_assert(sizeof(JitC) == " << j.consts.b.size() << ", \"LayeredConsts layout: host packer out of date\");\n";
+        src << "}\n";
+    }
     const std::string dir = lib_dir(), csrc = dir + "/csrc";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-I" + csrc};
     if (mode == SCG_MODE_FAST_F64) opts.push_back("--fmad=false");      // same contract as scg_sc_f64.cu
@@ -340,7 +352,7 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     unsigned long long h = 1469598103934665603ull;
     h = fnv1a(h, name); h = fnv1a(h, src.str());
     for (const auto& o : opts) if (o.compare(0, 2, "-I") != 0) h = fnv1a(h, o);
-    for (const char* f : {"/scg_common.cuh", "/scg_sc_device.cuh", "/scg_sc_static.cuh"}) {
+    for (const char* f : {"/scg_common.cuh", "/scg_sc_device.cuh", "/scg_sc_static.cuh", "/scg_sc_split.cuh"}) {
         std::string text;
         if (!read_file(csrc + f, text)) { set_error("jit: cannot read %s%s", csrc.c_str(), f); return SCG_ESTATE; }
         h = fnv1a(h, text);
@@ -422,6 +434,40 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     const size_t es = mode == SCG_MODE_FAST_F64 ? 8 : 4;
     if (f64) pack_consts<double>(hs, j.S, j.F, j.W, j.R, j.ML, j.consts);
     else pack_consts<float>(hs, j.S, j.F, j.W, j.R, j.ML, j.consts);
+    // Chains whose state overflows one thread's registers: G lanes per env (scg_sc_split.cuh).  G = the smallest power of
+    // two that leaves a lane at most 50 state values (measured on 5-4-7-10 and 10 per stage, profiles/r2_split_*.log:
+    // fewer lanes spill, more lanes idle on the echelons that are not a multiple of G); constant lead times, fp32 I/O.
+    // SCG_SPLIT_G / SCG_SPLIT_MINB override (experiments; G = 0 keeps the one-thread-per-env kernel).
+    // registers the one-thread-per-env kernel would need for its state: fp32 stocks + ring, or fp64 stocks + the 32-bit
+    // fixed-point ring of the mixed mode; measured to work up to ~165 (2-3-2-4, 3 products, lead time 3: 0.51 of the HBM peak)
+    const int np_all = hs.N * hs.P;
+    const int full_state_regs = f64 ? np_all * 2 + np_all * j.ML : np_all * (1 + j.ML);
+    if (!hs.stochL && es == 4 && full_state_regs > (f64 ? 180 : 150)) {
+        int g = 0;
+        for (int cand : {2, 4, 8}) {
+            const int kt = (j.S + cand - 1) / cand + (j.F + cand - 1) / cand + (j.W + cand - 1) / cand + (j.R + cand - 1) / cand;
+            g = cand;
+            if (kt * hs.P * (1 + j.ML) <= 50) break;
+        }
+        if (const char* e = getenv("SCG_SPLIT_G")) g = atoi(e);
+        if (g == 2 || g == 4 || g == 8) {
+            j.split_g = g;
+            const size_t wtile = (size_t)(32 / g) * (hs.A + hs.O) * es, budget_s = (size_t)227 * 1024 - 128 - 1024;
+            int warps = 4;
+            while (warps > 1 && (size_t)warps * wtile > budget_s / 2) warps >>= 1;
+            if (wtile <= budget_s) {
+                j.threads = 32 * warps;
+                j.smem = 128 + (size_t)warps * wtile;
+                // fp64 state with 4 or fewer lanes per env needs the whole register file (255 per thread); else 168
+                const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024)), by_regs = 65536 / (j.threads * ((f64 && g <= 4) ? 255 : 168));
+                int minb = by_smem < by_regs ? by_smem : by_regs;
+                if (const char* e = getenv("SCG_SPLIT_MINB")) minb = atoi(e);
+                j.minb = minb < 1 ? 1 : (minb > 16 ? 16 : minb);
+                return true;
+            }
+            j.split_g = 0;
+        }
+    }
     // the whole state should stay in registers; the warp tiles must fit shared memory
     const size_t tile = (size_t)32 * (hs.A + hs.O) * es, budget = (size_t)227 * 1024 - 128 - 1024;
     const int state_regs = hs.N * hs.P * (1 + j.ML) * (f64 ? 2 : 1);
@@ -473,8 +519,11 @@ int sc_jit_run(ScJit** cache, const ScRun& r) {
     int n_steps = r.n_steps;
     const void* actions = r.actions;
     void* obs = r.obs; void* reward = r.reward; unsigned char* done = r.done;
-    void* args[] = {(void*)j.consts.b.data(), const_cast<void*>(r.dev_spec), const_cast<void*>(r.state), &in, &n_steps, &actions, &obs, &reward, &done};
-    const unsigned blocks = (unsigned)((n + j.threads - 1) / j.threads);
+    void* args_layered[] = {(void*)j.consts.b.data(), const_cast<void*>(r.dev_spec), const_cast<void*>(r.state), &in, &n_steps, &actions, &obs, &reward, &done};
+    void* args_split[] = {const_cast<void*>(r.dev_spec), const_cast<void*>(r.state), &in, &n_steps, &actions, &obs, &reward, &done};
+    void** args = j.split_g > 0 ? args_split : args_layered;
+    const long long per_block = j.split_g > 0 ? (long long)j.threads / j.split_g : (long long)j.threads;      // envs per block
+    const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
     if (g_drv.LaunchKernel(k.fn, blocks, 1, 1, (unsigned)j.threads, 1, 1, (unsigned)j.smem, (CUstream)r.stream, args, nullptr) != CUDA_SUCCESS) {
         set_error("jit: cuLaunchKernel failed");
         return SCG_ECUDA;

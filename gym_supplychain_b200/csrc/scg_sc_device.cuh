@@ -56,6 +56,7 @@ struct ScDevSpec {
     const int* itime;       // [n_init]
     const Real* iamt;       // [n_init]
     const unsigned long long* lt_thr;   // [maxL] stochastic lead times: lt = 1 + #{j < maxL-1 : word >= lt_thr[j]}
+    const float *inv_cap, *inv_ms;      // [N*P] 1/stock_capacity, 1/max_ship (0 where max_ship == 0): fp32 obs of the split kernel
     const int* dkind;       // [P]
     const double *dlo, *dhi, *dstd, *dpeaks, *dminavg, *dmaxavg;   // [P]
 };
@@ -217,6 +218,7 @@ struct DynTopo {
     __device__ __forceinline__ int ebeg(int n) const { return sp.ebeg[n]; }
     __device__ __forceinline__ int ndest(int n) const { return sp.ebeg[n + 1] - sp.ebeg[n]; }
     __device__ __forceinline__ int edst(int e) const { return sp.edst[e]; }
+    __device__ __forceinline__ int dest_np(int e0, int i, int p) const { return sp.edst[e0 + i] * sp.P + p; }   // where edge e0+i delivers product p
     __device__ __forceinline__ Real ecap(int e) const { return sp.ecap[e]; }
     __device__ __forceinline__ Real ecost(int e, int p) const { return sp.ecost[e * sp.P + p]; }
     __device__ __forceinline__ Real proc_cap(int n) const { return sp.proc_cap[n]; }
@@ -263,6 +265,7 @@ struct RingGlobal {
     __device__ __forceinline__ void push(int np, int /*t*/, int lt, Real amount) {
         slot[((long long)np * ring + (lt - 1)) * n] += amount;
     }
+    __device__ __forceinline__ void push_own(int np, int t, int lt, Real amount) { push(np, t, lt, amount); }   // a supplier's own order
     template <class Tp>
     __device__ __forceinline__ void reset(const Tp& tp, const ScDevSpec<Real>& sp) {
         const int NP = sp.N * sp.P;
@@ -331,6 +334,7 @@ struct HeapGlobal {
         return got;
     }
     __device__ __forceinline__ void push(int np, int t, int lt_, double amount) { push_item(np, t + lt_, amount); }
+    __device__ __forceinline__ void push_own(int np, int t, int lt_, double amount) { push_item(np, t + lt_, amount); }
     template <class Tp>
     __device__ __forceinline__ void reset(const Tp& tp, const ScDevSpec<double>& sp) {     // :402-412
         const int NP = sp.N * sp.P;
@@ -441,8 +445,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                 if (tp.has_supply(n, p)) {
                     const Real amount = denorm_action<Real>(ar.get(ai)) * tp.sup_cap(n, p);
                     ++ai;
-                    if constexpr (Tp::kStatic && (SCG_TRIM & 32) && Lr::kConst) pp.push(n * P + p, t, lr.get(li), relu_loose<Real>(amount));
-                    else if (amount > (Real)0) { pp.push(n * P + p, t, lr.get(li), amount); ++li; }
+                    if constexpr (Tp::kStatic && (SCG_TRIM & 32) && Lr::kConst) pp.push_own(n * P + p, t, lr.get(li), relu_loose<Real>(amount));
+                    else if (amount > (Real)0) { pp.push_own(n * P + p, t, lr.get(li), amount); ++li; }
                     const Real sup = amount * tp.sup_cost(n, p);
                     cost += sup;
                     inf.add(INFO_SUPPLY, p, sup, amount);
@@ -544,8 +548,8 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     Real sc = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
                     for (int i = 0; i < D; ++i) {
-                        if constexpr (Tp::kStatic && (SCG_TRIM & 16)) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), relu_loose<Real>(send[i]));
-                        else if (send[i] > (Real)0) pp.push(tp.edst(e0 + i) * P + p, t, lr.get(base + i), send[i]);   // :344-348
+                        if constexpr (Tp::kStatic && (SCG_TRIM & 16)) pp.push(tp.dest_np(e0, i, p), t, lr.get(base + i), relu_loose<Real>(send[i]));
+                        else if (send[i] > (Real)0) pp.push(tp.dest_np(e0, i, p), t, lr.get(base + i), send[i]);   // :344-348
                         sc += send[i] * tp.ecost(e0 + i, p);                 // :352-353
                     }
                     cost += sc;

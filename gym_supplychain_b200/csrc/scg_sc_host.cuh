@@ -86,6 +86,12 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
     size_t o_dmin = put_dbl(hs.dminavg), o_dmax = put_dbl(hs.dmaxavg);
     const std::vector<unsigned long long> thr = sc_leadtime_thresholds(hs);
     size_t o_thr = put(thr.data(), thr.size() * sizeof(unsigned long long));
+    std::vector<float> inv_cap(hs.cap.size()), inv_ms(hs.cap.size());
+    for (size_t i = 0; i < hs.cap.size(); ++i) {
+        inv_cap[i] = hs.cap[i] > 0 ? (float)(1.0 / hs.cap[i]) : 0.0f;
+        inv_ms[i] = hs.max_ship[i] > 0 ? (float)(1.0 / hs.max_ship[i]) : 0.0f;
+    }
+    size_t o_icap = put(inv_cap.data(), inv_cap.size() * sizeof(float)), o_ims = put(inv_ms.data(), inv_ms.size() * sizeof(float));
 
     unsigned char* d = nullptr;
     SCG_CUDA(cudaMalloc(&d, buf.size()));
@@ -106,6 +112,7 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
     sp.dlo = SCG_P(double, o_dlo); sp.dhi = SCG_P(double, o_dhi); sp.dstd = SCG_P(double, o_dstd); sp.dpeaks = SCG_P(double, o_dpk);
     sp.dminavg = SCG_P(double, o_dmin); sp.dmaxavg = SCG_P(double, o_dmax);
     sp.lt_thr = SCG_P(unsigned long long, o_thr);
+    sp.inv_cap = SCG_P(float, o_icap); sp.inv_ms = SCG_P(float, o_ims);
 #undef SCG_P
     memcpy(devspec_out, &sp, sizeof(sp));
     *blob_out = d;

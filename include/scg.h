@@ -159,7 +159,8 @@ typedef struct ScgInfo {
     int32_t ring_depth;        /* FAST modes: slots per (node, product)                      */
     int32_t heap_capacity;     /* EXACT mode: entries per (node, product) queue              */
     int32_t kernel_variant;    /* 0 generic runtime-topology kernel, >0 a compile-time one   */
-                               /* (100: instantiated at run time for this chain's shape)     */
+                               /* (100: instantiated at run time for this chain's shape;     */
+                               /*  101: ditto, node-parallel kernel -- several lanes per env) */
     int32_t info_values;       /* 16*P when SCG_FLAG_BUILD_INFO, else 0                      */
     int64_t state_bytes;       /* size of the blob for scg_get_state / scg_set_state         */
 } ScgInfo;

@@ -181,3 +181,21 @@ def test_runtime_instantiation_compiles_without_a_gpu_and_rejects_non_layered_ch
     broken[first_supplier]["ship_capacity"] = broken[first_supplier]["ship_capacity"][:1]
     assert FlatSpec(broken, **kw2).precompile("fast_f32") is False
     assert fs.precompile("exact_f64") is False                                              # heapq-exact mode: runtime-topology kernel only
+
+
+def test_large_chains_get_the_node_parallel_kernel(tmp_path, monkeypatch):
+    """Chains whose state overflows one thread's registers (SupplyChainNPerStage([5,4,7,10]), the reference's golden-return
+    shape test_Nperstage.py:23-53) are instantiated as the node-parallel split kernel (G lanes per env, warp-shuffle sums of
+    the shipments per destination); mid-size chains keep the one-thread-per-env kernel.  NVRTC only: no GPU needed."""
+    from gym_supplychain_b200 import FlatSpec, presets
+    monkeypatch.setenv("SCG_JIT_CACHE", str(tmp_path))
+    monkeypatch.delenv("SCG_SPLIT_G", raising=False)
+    monkeypatch.delenv("SCG_SPLIT_MINB", raising=False)
+    info, kw = presets.n_per_stage(nodes_per_echelon=[5, 4, 7, 10])
+    assert FlatSpec(info, **kw).precompile("fast_f32") is True
+    names = [p.read_text() for p in tmp_path.iterdir() if p.name.endswith(".name")]
+    assert len(names) == 1 and "sc_split_rollout" in names[0]
+    info, kw = presets.n_per_stage(nodes_per_echelon=[2, 1, 2, 3], num_products=3, avg_leadtime=3, max_leadtime=3)
+    assert FlatSpec(info, **kw).precompile("fast_f32") is True
+    names = [p.read_text() for p in tmp_path.iterdir() if p.name.endswith(".name")]
+    assert len(names) == 2 and sum("sc_layered_rollout" in x for x in names) == 1

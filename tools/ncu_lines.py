@@ -14,8 +14,11 @@ base = int(rows[0][ia], 16)
 ex = {int(r[ia], 16) - base: (int(r[ie]), r[iss]) for r in rows if r[ie].isdigit()}
 # mangled-name match: take the function whose instruction count equals the report's
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+if obj.endswith(".cubin"):                      # a run-time instantiated kernel: the cubin of the JIT cache
+    cubin = os.path.abspath(obj)
+else:
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
+    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 funcs, cur, line = {}, None, None
 for l in dis.splitlines():
@@ -28,6 +31,10 @@ for l in dis.splitlines():
 cands = [k for k, v in funcs.items() if len(v) == len(ex)]
 want = re.sub(r"[^A-Za-z0-9]", "", kname.split("<")[0].split("::")[-1])
 cands = [k for k in cands if want in k] or cands
+if not cands:                                   # a cubin with one kernel (JIT cache): take it if the sizes are close
+    cands = [k for k, v in funcs.items() if want in re.sub(r"[^A-Za-z0-9]", "", k) and abs(len(v) - len(ex)) <= 0.05 * len(ex)]
+    if cands:
+        print("WARNING: %d SASS rows in the report, %d in the cubin: line attribution is approximate" % (len(ex), len(funcs[cands[0]])))
 f = funcs[cands[0]]
 per = Counter()
 for off, ln, txt in f:

@@ -51,6 +51,27 @@ def random_chain(job):
     return "random chain %d %s" % (seed, cnt), mode, False, ok, time.time() - t0
 
 
+def split_variant(job):
+    """Large chains (node-parallel split kernel) as tests/test_gpu_split.py instantiates them: default lane count, the other
+    lane counts, and the one-thread-per-env kernel they are compared with (SCG_SPLIT_G=0)."""
+    shape, mode, rand, g = job
+    from gym_supplychain_b200 import FlatSpec, presets
+    if g is None:
+        os.environ.pop("SCG_SPLIT_G", None)
+    else:
+        os.environ["SCG_SPLIT_G"] = str(g)
+    t0 = time.time()
+    info, k = presets.n_per_stage(nodes_per_echelon=shape)
+    ok = FlatSpec(info, **k).precompile(mode, in_kernel_actions=rand)
+    os.environ.pop("SCG_SPLIT_G", None)
+    return "%s G=%s" % (shape, g), mode, rand, ok, time.time() - t0
+
+
+SPLIT = [([5, 4, 7, 10], m, r, None) for m in ("mixed", "fast_f32") for r in (False, True)] + \
+        [(10, m, False, None) for m in ("mixed", "fast_f32")] + \
+        [([5, 4, 7, 10], "mixed", False, g) for g in (2, 8)] + [([5, 4, 7, 10], m, False, 0) for m in ("mixed", "fast_f32")]
+
+
 def main():
     from golden_util import sc_cases
     jobs = [(n, m, False) for n in sc_cases() for m in ("fast_f32", "mixed", "fast_f64")]
@@ -59,6 +80,8 @@ def main():
         for name, mode, rand, ok, dt in ex.map(one, jobs):
             print("%-28s %-9s %s %5.1fs" % (name, mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
         for name, mode, rand, ok, dt in ex.map(random_chain, [(c, m) for c in RANDOM_CHAINS for m in ("mixed", "fast_f64")]):
+            print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
+        for name, mode, rand, ok, dt in ex.map(split_variant, SPLIT):
             print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
         for name, mode, rand, ok, dt in ex.map(extra, xjobs):
             print("%-28s %-9s %s %5.1fs" % (name[:28], mode, "compile-time kernel ready" if ok else "runtime-topology kernel only", dt), flush=True)
