@@ -43,6 +43,7 @@ struct ScgEnv {
     ScState<double> st64{};
     int variant = 0;
     ScJit* jit = nullptr;           // run-time instantiated kernels (variant == SC_VARIANT_JIT)
+    std::vector<unsigned char> consts_cache;   // kernel-parameter image of the spec for the compile-time kernel
     // beer game
     BgHostSpec bhs;
     BgDevSpec bsp{};
@@ -256,7 +257,7 @@ static int sc_dispatch(ScgEnv* h, int op, int n_steps, const unsigned char* mask
     r.inj_demand = h->inj_demand; r.inj_leadtimes = h->inj_leadtimes;
     r.key = h->key; r.first_env = h->opt.first_env; r.auto_reset = h->opt.auto_reset;
     r.op = op; r.n_steps = n_steps; r.reset_mask = mask; r.actions = actions; r.obs = obs; r.reward = reward; r.done = done;
-    r.stream = stream; r.err = h->err;
+    r.stream = stream; r.err = h->err; r.consts_cache = &h->consts_cache; r.device = h->opt.device;
     ++h->launches;
     if (op == SC_OP_ROLLOUT && h->variant == SC_VARIANT_JIT) {
         if (sc_jit_run(&h->jit, r) == SCG_OK) return SCG_OK;

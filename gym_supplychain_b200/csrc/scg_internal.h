@@ -58,6 +58,8 @@ struct ScRun {
     unsigned char* done;
     cudaStream_t stream;
     int* err;                   // device word of sticky SCG_ERR_* bits (scg_status)
+    std::vector<unsigned char>* consts_cache;   // per handle: the kernel-parameter image of the spec, built on the first launch
+    int device;
 };
 
 // Implemented in scg_sc_f32.cu / scg_sc_f64.cu

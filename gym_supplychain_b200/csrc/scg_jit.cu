@@ -454,6 +454,7 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
             j.split_g = g;
             const size_t wtile = (size_t)(32 / g) * (hs.A + hs.O) * es, budget_s = (size_t)227 * 1024 - 128 - 1024;
             int warps = 4;
+            if (const char* e = getenv("SCG_SPLIT_WARPS")) warps = atoi(e) > 0 ? atoi(e) : 4;
             while (warps > 1 && (size_t)warps * wtile > budget_s / 2) warps >>= 1;
             if (wtile <= budget_s) {
                 j.threads = 32 * warps;

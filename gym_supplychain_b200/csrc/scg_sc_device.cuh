@@ -136,9 +136,9 @@ __device__ __forceinline__ int sc_leadtime(const ScDevSpec<Real>& sp, const ScIn
     if (in.inj_leadtimes) return checked_leadtime(in.inj_leadtimes[((long long)(t - 1) * sp.K + k) * n_envs + env], sp.maxL, in.err);
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
     Philox4 b = rng_block(in.key, genv, episode, (unsigned)t, STREAM_LEADTIME, (unsigned)(k >> 2));
-    const unsigned long long word = pick_word(b, k & 3);
+    const unsigned word = pick_word(b, k & 3);
     int lt = 1;                                      // 1 + Poisson(avg-1) clipped to maxL, by inverse CDF (:670-672)
-    for (int q = 0; q + 1 < sp.maxL; ++q) lt += (word >= sp.lt_thr[q]) ? 1 : 0;
+    for (int q = 0; q + 1 < sp.maxL; ++q) lt += (word > (unsigned)(sp.lt_thr[q] - 1ull)) ? 1 : 0;   // thr in [1, 2^32]
     return lt;
 }
 
@@ -494,7 +494,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 // out - (out - proc_left): a residue of 1e-13 where the reference has 0 flips
                                 // `send > 0` below, and with a negative ship capacity (F4a) that is a whole clip.
                                 const Real d = out[i] - proc_left, ex = relu_loose<Real>(d);
-                                over_proc += ex;
+                                over_proc = i == 0 ? ex : over_proc + ex;        // (0 + x is not folded by the compiler)
                                 out[i] = d > (Real)0 ? proc_left : out[i];
                                 proc_left -= relu_loose<Real>(out[i]);
                             } else {
@@ -513,7 +513,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                                 // no processing ratio: the capacity left never goes negative, so the clip is
                                 // ex = max(send - room, 0) and a clipped destination is left with no capacity
                                 const Real d = send[i] - room[i], ex = relu_loose<Real>(d);
-                                over_ship += ex;
+                                over_ship = i == 0 ? ex : over_ship + ex;
                                 send[i] -= ex;
                                 out[i] = send[i];
                                 room[i] = clear_if_positive_loose<Real>(room[i], d);
@@ -538,7 +538,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     }
                     Real leaving = (Real)0;
 #pragma unroll(Tp::kStatic ? MAXD : 1)
-                    for (int i = 0; i < D; ++i) leaving += out[i];           // :331
+                    for (int i = 0; i < D; ++i) leaving = (Tp::kStatic && i == 0) ? out[0] : leaving + out[i];   // :331
                     pp.set_stock(np, s - leaving);
                     if (factory) {                                           // :338
                         const Real pc = leaving * tp.proc_cost(n, p);
@@ -560,7 +560,7 @@ __device__ __forceinline__ Real sc_step_nodes(const Tp& tp, Pp& pp, int t, Ar& a
                     }
                 }
                 const Real ppen = tp.c_xproc() * over_proc, spen = tp.c_xship() * over_ship;
-                cost += ppen;                                                // :361
+                if (!Tp::kStatic || factory) cost += ppen;                   // :361 (over_proc is identically 0 elsewhere)
                 cost += spen;                                                // :366
                 inf.add(INFO_PROCESS_PEN, p, ppen, over_proc);
                 inf.add(INFO_SHIP_PEN, p, spen, over_ship);

@@ -194,23 +194,39 @@ static int sc_launch_layered(const ScRun& r) {
     using C = LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>;
     using Tp = LayeredTopo<Real, sizeof(Io) == 8, S, F, W, R, P, L, ML, STOCH>;
     static_assert(sizeof(C) <= 3800, "constants must fit the kernel parameter bank");
-    C c;
-    sc_fill_consts<Real, S, F, W, R, P, L, ML, STOCH>(*r.hs, c);
+    // The constant block depends only on the handle's spec: built on the first launch, reused afterwards (the step()
+    // API launches once per period -- rebuilding it cost more host time than the launch itself).
+    C local;
+    const C* cp = &local;
+    if (r.consts_cache && r.consts_cache->size() == sizeof(C)) {
+        cp = reinterpret_cast<const C*>(r.consts_cache->data());
+    } else {
+        sc_fill_consts<Real, S, F, W, R, P, L, ML, STOCH>(*r.hs, local);
+        if (r.consts_cache) {
+            r.consts_cache->assign(reinterpret_cast<const unsigned char*>(&local), reinterpret_cast<const unsigned char*>(&local) + sizeof(C));
+            cp = reinterpret_cast<const C*>(r.consts_cache->data());
+        }
+    }
+    const C& c = *cp;
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
     const size_t smem = 128 + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
-    if (r.actions == nullptr) {
+    static unsigned long long attr_set[2] = {0ull, 0ull};         // [random actions?] bit d: shared-memory size set on device d
+    const int rnd = r.actions == nullptr ? 1 : 0;
+    const bool need_attr = r.device < 0 || r.device >= 64 || !((attr_set[rnd] >> r.device) & 1ull);
+    if (rnd) {
         auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, ML, STOCH, true, THREADS, MINB>;
-        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (need_attr) SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, nullptr, (Io*)r.obs, (Io*)r.reward, r.done);
     } else {
         auto k = sc_layered_rollout<Real, Io, S, F, W, R, P, L, ML, STOCH, false, THREADS, MINB>;
-        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (need_attr) SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<blocks, THREADS, smem, r.stream>>>(c, sp, st, in, r.n_steps, (const Io*)r.actions, (Io*)r.obs, (Io*)r.reward, r.done);
     }
+    if (need_attr && r.device >= 0 && r.device < 64) attr_set[rnd] |= 1ull << r.device;
     SCG_CUDA(cudaGetLastError());
     return SCG_OK;
 }
@@ -247,7 +263,12 @@ static int sc_launch_generic(const ScRun& r) {
 #define SCG_GEN_LAUNCH(REAL, IO, MODE_, INFO_)                                                                         \
     do {                                                                                                               \
         auto k = sc_generic_kernel<REAL, IO, MODE_, INFO_>;                                                            \
-        SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+        static size_t smem_set[64] = {0};                /* largest shared-memory size granted so far, per device */    \
+        const bool known = r.device >= 0 && r.device < 64;                                                             \
+        if (!known || smem_set[r.device] < smem) {                                                                     \
+            SCG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+            if (known) smem_set[r.device] = smem;                                                                      \
+        }                                                                                                              \
         k<<<blocks, threads, smem, r.stream>>>(sp, st, in, n_steps, r.reset_mask, do_reset, (const IO*)r.actions,      \
                                                (IO*)r.obs, (IO*)r.reward, r.done, use_smem, stage_io);                 \
     } while (0)

@@ -289,6 +289,9 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
+#if SCG_SYNC_PERIOD
+        __syncthreads();                   // keep the block's warps in the same stretch of the (larger than I-cache) loop body
+#endif
         if (bulk_in) {
             if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
             while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}

@@ -17,6 +17,9 @@
 
 namespace scg {
 
+#ifndef SCG_SYNC_PERIOD
+#define SCG_SYNC_PERIOD 0       // experiment: a block barrier per period (shared instruction fetches for loops beyond the I-cache)
+#endif
 #ifndef SCG_FIXED_RING
 #define SCG_FIXED_RING 1        // mixed mode, constant lead time: in-transit material as 32-bit fixed point (RingFixed)
 #endif
@@ -454,9 +457,12 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 
     // bulk (TMA) copies need 16-byte aligned addresses and sizes; otherwise fall back to plain warp copies
     const unsigned act_bytes = (unsigned)(n_here * A * (int)sizeof(Io)), obs_bytes = (unsigned)(n_here * O * (int)sizeof(Io));
-    const bool bulk_in = !RANDOM_ACT && n_here > 0 && (((size_t)actions) & 15) == 0 &&
+#ifndef SCG_NO_BULK
+#define SCG_NO_BULK 0           // experiment: plain warp copies instead of the bulk (TMA) copies (bank-conflict attribution)
+#endif
+    const bool bulk_in = !SCG_NO_BULK && !RANDOM_ACT && n_here > 0 && (((size_t)actions) & 15) == 0 &&
                          (((size_t)n * A * sizeof(Io)) & 15) == 0 && (act_bytes & 15) == 0 && ((32 * A * sizeof(Io)) & 15) == 0;
-    const bool bulk_out = obs != nullptr && n_here > 0 && (((size_t)obs) & 15) == 0 && (((size_t)n * O * sizeof(Io)) & 15) == 0 &&
+    const bool bulk_out = !SCG_NO_BULK && obs != nullptr && n_here > 0 && (((size_t)obs) & 15) == 0 && (((size_t)n * O * sizeof(Io)) & 15) == 0 &&
                           (obs_bytes & 15) == 0 && ((32 * (A + O) * sizeof(Io)) & 15) == 0;
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
@@ -503,6 +509,9 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const long long io0 = (long long)s * n + env0;
+#if SCG_SYNC_PERIOD
+        __syncthreads();                   // keep the block's warps in the same stretch of the (larger than I-cache) loop body
+#endif
         if (bulk_in) {
             // tile s was requested one period ago (or in the prologue); ask L2 for tile s+1 now
             if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
@@ -541,10 +550,11 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                         for (int j = 0; j < 4; ++j) {
                             const int k = 4 * b + j;
                             if (k < K) {
-                                const unsigned long long word = pick_word(blk, j);
+                                // word >= thr with thr in [1, 2^32] ("never" = 2^32)  <=>  word > thr - 1 in 32 bits
+                                const unsigned word = pick_word(blk, j);
                                 int lt = 1;
 #pragma unroll
-                                for (int q = 0; q + 1 < ML; ++q) lt += (word >= c.lt_thr[q]) ? 1 : 0;
+                                for (int q = 0; q + 1 < ML; ++q) lt += (word > (unsigned)(c.lt_thr[q] - 1ull)) ? 1 : 0;
                                 lr.set(k, lt);
                             }
                         }

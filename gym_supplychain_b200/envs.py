@@ -257,6 +257,13 @@ class SupplyChainEnv(_ScgEnvBase):
             mode = "exact_f64" if num_envs is None else "fast_f32"
         if auto_reset is None:
             auto_reset = num_envs is not None
+        if mode != "exact_f64":
+            hits = self.flat.negative_ship_capacity_reachable()
+            if hits:
+                import warnings
+                warnings.warn("mode %r on a chain where a saturated factory edge can reach a negative ship capacity (reference "
+                              "quirk, supplychain_env.py:316-328; e.g. %s product %d -> %s): from there on only mode 'exact_f64' "
+                              "follows the reference step for step" % ((mode,) + hits[0]), RuntimeWarning, stacklevel=3)
         torch = _torch()
         self._io_dtype = torch.float32 if mode in ("fast_f32", "mixed") else torch.float64
         self._init_handle(_lib.load().scg_sc_create, self.flat.c_struct(), num_envs, device, mode, auto_reset, seed, first_env,

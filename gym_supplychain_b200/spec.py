@@ -148,6 +148,27 @@ class FlatSpec(object):
         self._keep = keep
         return s
 
+    def negative_ship_capacity_reachable(self):
+        """Can the reference's ship-capacity quirk (supplychain_env.py:316-328) leave a factory edge with a
+        NEGATIVE capacity for the next product?  It needs a multi-product factory whose processing ratio exceeds 1 and an
+        edge it can saturate: the most it can send is min(stock_capacity, processing_capacity) / ratio (:298-310).  From
+        then on whether an amount counts as `> 0` decides a whole clip, so only `exact_f64` follows the reference step
+        for step; the tolerance modes may diverge on such specs.  None of the reference's presets can
+        reach it.  Returns the list of (node name, product, edge destination name) that can."""
+        hits = []
+        if self.P < 2:
+            return hits
+        for n in range(self.N):
+            pcap = self.processing_capacity[n]
+            if not pcap > 0:
+                continue
+            for e in range(self.edge_begin[n], self.edge_begin[n + 1]):
+                for p in range(self.P):
+                    r = self.processing_ratio[n, p]
+                    if r > 1 and min(self.stock_capacity[n, p], pcap) / r > self.edge_ship_capacity[e]:
+                        hits.append((self.node_names[n], p, self.node_names[self.edge_dest[e]]))
+        return hits
+
     def precompile(self, mode="fast_f32", in_kernel_actions=False):
         """Make sure a compile-time kernel exists for this chain before the first rollout (needs no GPU): chains without a
         pre-built instantiation get one compiled with NVRTC into the on-disk cache (scg_sc_precompile).  Returns False

@@ -24,8 +24,23 @@ def main():
     mine = returns[first:first + n_local]
     local = torch.tensor([len(mine), mine.sum(), (mine ** 2).sum(), mine.min(), mine.max()], dtype=torch.float64)
     glob = allreduce_return_stats(local)
+    # bench.py's overlapped exchange: the all-gather of step k is consumed after step k+1 was submitted; the folded
+    # totals must equal the plain all-reduce of the summed per-step records
+    import bench
+
+    class Ctx(object):
+        pass
+    ctx = Ctx()
+    ctx.torch, ctx.dist, ctx.world, ctx.rank, ctx.dev = torch, dist, world, rank, torch.device("cpu")
+    xch = bench.StatsExchange(ctx)
+    chunks = np.array_split(mine, 5)
+    for c in chunks:
+        rec = torch.tensor([len(c), c.sum(), (c ** 2).sum(), c.min(), c.max()], dtype=torch.float64)
+        xch.consume(xch.submit(rec))                  # start this step's exchange, fold the previous one
+    pending_before_drain = xch.pending is not None
+    xch.drain()
     res = {"rank": rank, "world": world, "first": first, "n_local": n_local, "global": glob.tolist(),
-           "summary": list(summarize_stats(glob))}
+           "summary": list(summarize_stats(glob)), "overlapped": xch.total.tolist(), "pending_before_drain": pending_before_drain}
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
         json.dump(res, f)
     dist.barrier()

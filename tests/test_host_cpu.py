@@ -199,3 +199,18 @@ def test_large_chains_get_the_node_parallel_kernel(tmp_path, monkeypatch):
     assert FlatSpec(info, **kw).precompile("fast_f32") is True
     names = [p.read_text() for p in tmp_path.iterdir() if p.name.endswith(".name")]
     assert len(names) == 2 and sum("sc_layered_rollout" in x for x in names) == 1
+
+
+def test_negative_ship_capacity_diagnostic():
+    """The tolerance modes cannot follow the reference once a factory edge went negative: the host layer says
+    which specs can get there.  None of the reference's presets can; a multi-product factory with small edges can."""
+    from gym_supplychain_b200 import FlatSpec, presets
+    for info, kw in (presets.n_per_stage(nodes_per_echelon=3), presets.n_per_stage(nodes_per_echelon=[5, 4, 7, 10], num_products=4),
+                     presets.multi_product(), presets.multi_product_increasing_costs(num_products=3), presets.two_per_stage(),
+                     presets.main_demo_chain()):
+        assert FlatSpec(info, **kw).negative_ship_capacity_reachable() == []
+    info, kw = presets.n_per_stage(nodes_per_echelon=2, ship_capacity={"suppliers": [1000, 1000], "factories": [100, 100], "wholesalers": [1000, 1000]})
+    hits = FlatSpec(info, **kw).negative_ship_capacity_reachable()
+    assert hits and all(h[0].startswith("Factory") for h in hits)
+    info, kw = presets.n_per_stage(nodes_per_echelon=2, num_products=1, ship_capacity={"suppliers": [1000, 1000], "factories": [100, 100], "wholesalers": [1000, 1000]})
+    assert FlatSpec(info, **kw).negative_ship_capacity_reachable() == []          # one product: nothing comes after the clip
