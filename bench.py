@@ -786,7 +786,7 @@ def c4s_shape(world):
 def cpu_reference_block(cfg, cores, budget_s):
     """Bounded sample of the reference for config `cfg` on all host cores (rank 0, N=1): after a warm-up map (imports, first
     reset) each env family runs whole episodes, map after map, until `budget_s` seconds of wall time are spent on it."""
-    eps_per_map = {"ntom": 2, "linear": 12, "2perstage": 6, "supplychain-v0": 1, "beergame-v0": 100, "beergame-v2-stochastic": 40}
+    eps_per_map = {"ntom": 8, "linear": 48, "2perstage": 24, "supplychain-v0": 2, "beergame-v0": 400, "beergame-v2-stochastic": 160}
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         per = []

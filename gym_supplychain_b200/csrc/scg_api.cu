@@ -338,6 +338,7 @@ int scg_sc_create(const ScgSupplyChainSpec* spec, const ScgOptions* opt, ScgHand
     h->variant = opt->mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(h->hs)
                : opt->mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(h->hs)
                : opt->mode == SCG_MODE_MIXED ? sc_match_variant_mixed(h->hs) : 0;
+    if (const char* e = getenv("SCG_JIT_FORCE")) if (e[0] == '1') h->variant = 0;      // experiments: ignore the pre-built kernels
     if (h->variant == 0 && sc_jit_match(h->hs, opt->mode)) h->variant = SC_VARIANT_JIT;
     if (opt->flags & (SCG_FLAG_FORCE_GENERIC | SCG_FLAG_BUILD_INFO)) h->variant = 0;
     ScgInfo& I = h->info;
@@ -360,7 +361,8 @@ int scg_sc_precompile(const ScgSupplyChainSpec* spec, int32_t mode, int32_t in_k
     if (rc != SCG_OK) return rc;
     const int v = mode == SCG_MODE_FAST_F32 ? sc_match_variant_f32(hs) : mode == SCG_MODE_FAST_F64 ? sc_match_variant_f64(hs)
                 : mode == SCG_MODE_MIXED ? sc_match_variant_mixed(hs) : 0;
-    if (v > 0) return SCG_OK;                                   // already in the library
+    const char* force = getenv("SCG_JIT_FORCE");
+    if (v > 0 && !(force && force[0] == '1')) return SCG_OK;    // already in the library
     return sc_jit_precompile(hs, mode, in_kernel_actions != 0);
 }
 

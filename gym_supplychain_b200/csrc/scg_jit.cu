@@ -131,11 +131,22 @@ unsigned long long fnv1a(unsigned long long h, const std::string& s) {
 // generated translation unit static_asserts the size and a handful of offsets, so a drift between this packer and the
 // struct is a JIT compile error (-> fallback), never a silent mismatch.
 // ---------------------------------------------------------------------------------------
+static void init_text(std::string& out, double v) { char t[64]; snprintf(t, sizeof(t), "%.17g", v); out += t; if (!strpbrk(t, ".enai")) out += ".0"; out += ","; }
+static void init_text(std::string& out, float v) { char t[64]; snprintf(t, sizeof(t), "%.9g", (double)v); out += t; if (!strpbrk(t, ".enai")) out += ".0"; out += "f,"; }
+static void init_text(std::string& out, int v) { out += std::to_string(v) + ","; }
+static void init_text(std::string& out, unsigned long long v) { out += std::to_string(v) + "ull,"; }
+
 struct Packed {
     std::vector<unsigned char> b;
     size_t max_align = 1;
     std::vector<std::pair<std::string, size_t>> marks;
+    std::string init;                    // the same values as a flat aggregate initializer, member order (brace elision)
+    bool finite = true;
     template <class T> size_t put(const char* name, const T* v, size_t count) {
+        for (size_t i = 0; i < count; ++i) {
+            init_text(init, v[i]);
+            if (!(v[i] == v[i]) || (double)v[i] > 1e300 || (double)v[i] < -1e300) finite = false;
+        }
         const size_t al = alignof(T);
         if (al > max_align) max_align = al;
         size_t off = (b.size() + al - 1) / al * al;
@@ -276,6 +287,7 @@ struct ScJit {
     bool failed = false;
     int S = 0, F = 0, W = 0, R = 0, ML = 0, threads = 0, minb = 0;
     int split_g = 0;           // > 0: the node-parallel kernel (scg_sc_split.cuh) with that many lanes per env
+    bool baked = false;        // the spec's constants are compile-time constants of the instantiation (SCG_JIT_BAKE=1)
     size_t smem = 0;
     Packed consts;
     JitKernel k[2];            // [random actions ?]
@@ -328,6 +340,7 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     const char* io = mode == SCG_MODE_FAST_F64 ? "double" : "float";
     char name[512];
     std::ostringstream src;
+    std::string baked_inc;
     if (j.split_g > 0) {
         snprintf(name, sizeof(name), "scg::sc_split_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %d, %d>", real, io, j.S, j.F, j.W, j.R,
                  hs.P, hs.avgL, j.split_g, random_act ? "true" : "false", j.threads, j.minb);
@@ -335,8 +348,16 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     } else {
         snprintf(name, sizeof(name), "scg::sc_layered_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %s, %d, %d>", real, io, j.S, j.F, j.W,
                  j.R, hs.P, hs.avgL, j.ML, hs.stochL ? "true" : "false", random_act ? "true" : "false", j.threads, j.minb);
-        src << "#include \"scg_sc_static.cuh\"\nnamespace scg {\nusing JitC = LayeredConsts<" << real << ", " << j.S << ", " << j.F << ", " << j.W
-            << ", " << j.R << ", " << hs.P << ", " << hs.avgL << ", " << j.ML << ", " << (hs.stochL ? "true" : "false") << ">;\n"
+        std::ostringstream ctype;
+        ctype << "LayeredConsts<" << real << ", " << j.S << ", " << j.F << ", " << j.W << ", " << j.R << ", " << hs.P << ", " << hs.avgL
+              << ", " << j.ML << ", " << (hs.stochL ? "true" : "false") << ">";
+        if (j.baked) {
+            // the spec's constants become compile-time constants of this instantiation (immediate operands, folded
+            // products): the kernel reads kBaked instead of its parameter block
+            baked_inc = "namespace scg { __device__ constexpr " + ctype.str() + " kBaked = {" + j.consts.init + "}; }\n";
+            src << "#define SCG_BAKED_CONSTS_INC \"scg_baked.inc\"\n";
+        }
+        src << "#include \"scg_sc_static.cuh\"\nnamespace scg {\nusing JitC = " << ctype.str() << ";\n"
             << "static_assert(sizeof(JitC) == " << j.consts.b.size() << ", \"LayeredConsts layout: host packer out of date\");\n";
         src << "}\n";
     }
@@ -350,7 +371,7 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
 
     // cache key: everything that determines the cubin
     unsigned long long h = 1469598103934665603ull;
-    h = fnv1a(h, name); h = fnv1a(h, src.str());
+    h = fnv1a(h, name); h = fnv1a(h, src.str()); h = fnv1a(h, baked_inc);
     for (const auto& o : opts) if (o.compare(0, 2, "-I") != 0) h = fnv1a(h, o);
     for (const char* f : {"/scg_common.cuh", "/scg_sc_device.cuh", "/scg_sc_static.cuh", "/scg_sc_split.cuh"}) {
         std::string text;
@@ -369,7 +390,10 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     if (!(read_file(f_cubin, cubin) && read_file(f_name, lowered) && !cubin.empty() && !lowered.empty())) {
         fprintf(stderr, "[scg] compiling %s for this chain shape (NVRTC, once; cached under %s)\n", name, cache.c_str());
         void* prog = nullptr;
-        if (g_rtc.CreateProgram(&prog, src.str().c_str(), "scg_jit.cu", 0, nullptr, nullptr) != 0) { set_error("jit: nvrtcCreateProgram failed"); return SCG_ESTATE; }
+        const char* inc_src[1] = {baked_inc.c_str()};
+        const char* inc_name[1] = {"scg_baked.inc"};
+        if (g_rtc.CreateProgram(&prog, src.str().c_str(), "scg_jit.cu", baked_inc.empty() ? 0 : 1, baked_inc.empty() ? nullptr : inc_src,
+                                baked_inc.empty() ? nullptr : inc_name) != 0) { set_error("jit: nvrtcCreateProgram failed"); return SCG_ESTATE; }
         g_rtc.AddNameExpression(prog, name);
         std::vector<const char*> copts;
         for (const auto& o : opts) copts.push_back(o.c_str());
@@ -469,10 +493,15 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
             j.split_g = 0;
         }
     }
+    if (const char* e = getenv("SCG_JIT_BAKE")) j.baked = e[0] == '1' && j.consts.finite;
     // the whole state should stay in registers; the warp tiles must fit shared memory
     const size_t tile = (size_t)32 * (hs.A + hs.O) * es, budget = (size_t)227 * 1024 - 128 - 1024;
-    const int state_regs = hs.N * hs.P * (1 + j.ML) * (f64 ? 2 : 1);
+    // state registers: fp32 stocks + ring; fp64 stocks + 32-bit fixed-point ring (mixed, constant lead time); else all fp64
+    const bool fixed_ring = f64 && es == 4 && !hs.stochL;
+    const int state_regs = fixed_ring ? np_all * 2 + np_all * j.ML : np_all * (1 + j.ML) * (f64 ? 2 : 1);
     int regs = (state_regs + 88 + 7) / 8 * 8;
+    // an fp64-state kernel beyond 168 registers wants the whole file: it lives on instruction-level parallelism
+    if (f64 && regs > 168) regs = 255;
     regs = regs < 64 ? 64 : (regs > 255 ? 255 : regs);
     int warps = regs > 168 ? 2 : 4;
     while (warps > 1 && (size_t)warps * tile > budget) warps >>= 1;

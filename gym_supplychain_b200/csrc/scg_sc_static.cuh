@@ -45,6 +45,12 @@ struct LayeredConsts {
     int T;
 };
 
+}  // namespace scg
+#ifdef SCG_BAKED_CONSTS_INC     // run-time instantiation with the spec's constants baked in: defines scg::kBaked
+#include SCG_BAKED_CONSTS_INC
+#endif
+namespace scg {
+
 // EXACT = true keeps IEEE divisions (fp64 I/O modes: obs/rewards comparable bit-for-bit with the generic
 // fp64 kernel); false multiplies by host-computed reciprocals (fp32 and mixed modes).
 template <class Real, bool EXACT, int S, int F, int W, int R, int P_, int L_, int ML_, bool STOCH_>
@@ -434,10 +440,15 @@ __global__ void __maxnreg__(SCG_MAXNREG)
 #else
 __global__ void __launch_bounds__(THREADS, MINB)
 #endif
-sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH> c, ScDevSpec<Real> sp, ScState<Real> st,
+sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH> c_arg, ScDevSpec<Real> sp, ScState<Real> st,
                    ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
                    Io* __restrict__ reward, unsigned char* __restrict__ done) {
     constexpr bool kExact = sizeof(Io) == 8;
+#ifdef SCG_BAKED_CONSTS_INC
+    const LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>& c = kBaked;        // compile-time constants of THIS spec
+#else
+    const LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>& c = c_arg;         // the kernel parameter block
+#endif
     using Tp = LayeredTopo<Real, kExact, S, F, W, R, P, L, ML, STOCH>;
     constexpr int K = Tp::kK;
     constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
