@@ -248,6 +248,8 @@ static int sc_launch_generic(const ScRun& r) {
     int threads = 128, use_smem = 0, stage_io = 0;
     // copying the state into shared memory and back only pays when it is reused over several periods: reset() and
     // the single-period step() touch every element about once and work on HBM directly
+    // (also measured for the drop-in single env, where every access is a dependent one: no gain, 182 us per ntom step either
+    // way -- one thread's instruction latency, not the L2 round trips, is what a single heapq-exact env waits for)
     const bool want_smem = n_steps >= 3;
     for (int th : {128, 64, 32}) {
         if (!want_smem) break;

@@ -171,8 +171,25 @@ __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real
             pr[1] = prev_of(c01, !c12, c02, cpd[0], cpd[2]);
             pr[2] = prev_of(c02, c12, c01, cpd[0], cpd[1]);
         }
+    } else if constexpr (sizeof(RawT) == 4 && D <= 4 && sizeof(Real) == 8) {
+        // D = 4, fp32 actions, fp64 state: the predecessor's value is the largest capped action of those before i (a compare,
+        // a select and an FMNMX per ordered pair); "nobody before i" stays a separate case, as above.  (The pairwise form
+        // below keeps D running maxima alive at once: measured to spill at D = 4 in the fp64-state kernels -- 4-4-4-4 7.0 ms
+        // against 8.7 -- while the fp32 kernels prefer it, 5.2 ms against 5.6.)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const RawT none = __int_as_float((int)0xff800000u);          // -inf
+            RawT m = none;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (j == i) continue;
+                const bool before = (j < i) ? (r[j] <= r[i]) : (r[j] < r[i]);
+                m = fmaxf(m, before ? cpd[j] : none);
+            }
+            pr[i] = m == none ? (RawT)-1 : m;
+        }
     } else if constexpr (sizeof(RawT) == 4) {
-        // any D, fp32 actions: the predecessor's value is the largest capped action of those before i.  ONE compare per
+        // larger D, fp32 actions: the predecessor's value is the largest capped action of those before i.  ONE compare per
         // unordered pair {a < b} decides both directions (a before b, ties to the lower index -- else b before a), each
         // side then takes a conditional max: 3 instructions per pair instead of 6.  "Nobody before i" stays a separate
         // case (-inf sentinel), as above.
@@ -180,14 +197,17 @@ __device__ __forceinline__ void ship_cuts_static(const RawT* r, Real limit, Real
         RawT m[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) m[i] = none;
+        // (rectangular loops with a folded guard: a triangular `b = a + 1` nest is not always fully unrolled, and one
+        // surviving run-time index demotes the whole env state to local memory)
 #pragma unroll
         for (int a = 0; a < D; ++a)
 #pragma unroll
-            for (int b = a + 1; b < D; ++b) {
-                const bool ab = r[a] <= r[b];
-                m[b] = ab ? fmaxf(m[b], cpd[a]) : m[b];
-                m[a] = ab ? m[a] : fmaxf(m[a], cpd[b]);
-            }
+            for (int b = 0; b < D; ++b)
+                if (b > a) {
+                    const bool ab = r[a] <= r[b];
+                    m[b] = ab ? fmaxf(m[b], cpd[a]) : m[b];
+                    m[a] = ab ? m[a] : fmaxf(m[a], cpd[b]);
+                }
 #pragma unroll
         for (int i = 0; i < D; ++i) pr[i] = m[i] == none ? (RawT)-1 : m[i];
     } else {

@@ -106,3 +106,53 @@ def test_split_kernel_chunked_rollouts_steps_and_random_policy(mode):
     assert a.scg_info.kernel_variant == 101
     ra, rb = a.rollout(30), b.rollout(30)                           # in-kernel uniform random actions
     assert all(torch.equal(x, y) for x, y in zip(ra, rb)) and torch.isfinite(ra[1]).all() and float(ra[0].abs().max()) <= 1.0
+
+
+def _randomise_constants(rs, info, P, L):
+    """Per-NODE and per-EDGE random constants (the presets give every node of an echelon the same numbers, which would hide
+    a wrong node / edge index in the lanes' constant lookups).  Factories keep ship capacities they cannot exceed (the F4a
+    regime only `exact_f64` can follow, see test_gpu_c_oracle._random_layered_chain)."""
+    ri = lambda lo, hi, n: [int(x) for x in rs.randint(lo, hi, n)]              # noqa: E731
+    for nd in info.values():
+        nd["stock_capacity"] = ri(400, 3000, P)
+        nd["initial_stock"] = [int(rs.randint(0, c)) for c in nd["stock_capacity"]]
+        nd["stock_cost"] = ri(1, 4, P)
+        if "supply_capacity" in nd:
+            nd["supply_capacity"], nd["supply_cost"] = ri(100, 900, P), ri(1, 9, P)
+            nd["initial_supply"] = [ri(0, 500, L) for _ in range(P)]
+        else:
+            nd["initial_shipments"] = [ri(0, 500, L) for _ in range(P)]
+        if "processing_capacity" in nd:
+            nd["processing_capacity"], nd["processing_cost"] = int(rs.randint(300, 2500)), ri(1, 15, P)
+        if "destinations" in nd:
+            D = len(nd["destinations"])
+            nd["dest_costs"], nd["ship_capacity"] = [ri(1, 6, D) for _ in range(P)], ri(150, 1500, D)
+            if "processing_capacity" in nd:
+                nd["ship_capacity"] = [c + 2 * max(nd["stock_capacity"]) for c in nd["ship_capacity"]]
+
+
+@pytest.mark.parametrize("shape,P,L,seed", [(BIG, 2, 2, 1), ([6, 5, 9, 7], 2, 2, 2), ([4, 6, 5, 8], 3, 2, 3), ([7, 3, 6, 9], 2, 3, 4)])
+@pytest.mark.parametrize("mode,rtol,oatol", [("mixed", 1e-6, 5e-7), ("fast_f32", 2e-5, 5e-6)])
+def test_split_kernel_with_random_per_node_constants_vs_c_oracle(shape, P, L, seed, mode, rtol, oatol):
+    """Large layered chains with every capacity, cost, initial stock and initial shipment drawn per node / per edge, a
+    per-product processing ratio, three products, lead time 3: the lanes' constant lookups (node, product, edge) and the
+    ownership of echelons that are not a multiple of the lane count are all exercised."""
+    rs = np.random.RandomState(7000 + seed)
+    T, n = 40, 45
+    info, kw = presets.n_per_stage(nodes_per_echelon=shape, num_products=P, avg_leadtime=L, max_leadtime=L, total_time_steps=T,
+                                   demand_range=(0, int(rs.randint(50, 400))), unmet_demand_cost=int(rs.randint(20, 300)),
+                                   exceeded_stock_capacity_cost=int(rs.randint(2, 20)), exceeded_process_capacity_cost=int(rs.randint(2, 20)),
+                                   exceeded_ship_capacity_cost=int(rs.randint(2, 20)), processing_ratio=[int(x) for x in rs.randint(1, 4, P)])
+    _randomise_constants(rs, info, P, L)
+    okw = {k: v for k, v in kw.items() if k not in ("seed", "build_info")}
+    cc = CSupplyChainOracle(info, **okw)
+    dem, lts, a = _inputs(rs, cc, n, T, kw["demand_range"][0], kw["demand_range"][1], wide=(seed % 2 == 0))
+    ref = _oracle_run(cc, dem, lts, a, canonical=True)
+    env = gsc.SupplyChainEnv(info, num_envs=n, mode=mode, auto_reset=False, **okw)
+    assert env.scg_info.kernel_variant == 101, shape
+    got = _gpu_run(env, dem, lts, a)
+    assert env.scg_info.kernel_variant == 101, "the run-time instantiation failed and fell back"
+    assert np.array_equal(got[2], ref[2])
+    rel = np.abs(got[1] - ref[1]) / np.maximum(np.abs(ref[1]), 1.0)
+    assert rel.max() <= rtol, (shape, mode, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+    assert np.abs(got[0] - ref[0]).max() <= oatol, (shape, mode)

@@ -214,3 +214,33 @@ def test_negative_ship_capacity_diagnostic():
     assert hits and all(h[0].startswith("Factory") for h in hits)
     info, kw = presets.n_per_stage(nodes_per_echelon=2, num_products=1, ship_capacity={"suppliers": [1000, 1000], "factories": [100, 100], "wholesalers": [1000, 1000]})
     assert FlatSpec(info, **kw).negative_ship_capacity_reachable() == []          # one product: nothing comes after the clip
+
+
+@pytest.mark.parametrize("kw,mode", [
+    (dict(nodes_per_echelon=[2, 3, 2, 4], num_products=3, avg_leadtime=3, max_leadtime=3), "mixed"),
+    (dict(nodes_per_echelon=[5, 4, 7, 10]), "fast_f32"),
+    (dict(nodes_per_echelon=4), "mixed"),
+])
+def test_instantiated_kernels_keep_the_env_state_in_registers(tmp_path, monkeypatch, kw, mode):
+    """A run-time index that survives unrolling silently moves the WHOLE env state to local memory (seen twice while
+    writing the kernels: a 10x slowdown with no spill reported).  Guard: the stack frame of the instantiated kernels stays
+    what honest register spills need (cuobjdump --dump-resource-usage of the cached cubin; no GPU needed)."""
+    import re
+    import shutil
+    import subprocess
+    from gym_supplychain_b200 import FlatSpec, presets
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    monkeypatch.setenv("SCG_JIT_CACHE", str(tmp_path))
+    for v in ("SCG_SPLIT_G", "SCG_SPLIT_MINB", "SCG_JIT_BAKE", "SCG_JIT_FORCE", "SCG_JIT_DEFINES"):
+        monkeypatch.delenv(v, raising=False)
+    info, k = presets.n_per_stage(**kw)
+    assert FlatSpec(info, **k).precompile(mode) is True
+    cubins = [p for p in tmp_path.iterdir() if p.name.endswith(".cubin")]
+    assert len(cubins) == 1
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", str(cubins[0])], capture_output=True, text=True).stdout
+    m = re.search(r"REG:(\d+) STACK:(\d+)", out)
+    assert m, out[-400:]
+    regs, stack = int(m.group(1)), int(m.group(2))
+    assert stack <= 700, "kernel state demoted to local memory? REG %d STACK %d" % (regs, stack)

@@ -1,9 +1,9 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/r2_gputest13.log 2>&1; tail -4 gpurun_out/r2_gputest13.log
+timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/r2_gputest14.log 2>&1; tail -4 gpurun_out/r2_gputest14.log; timeout 600 python tools/split_check.py --configs 4:0,8:0 > gpurun_out/r2_split3.log 2>&1; grep -v "^\[scg\]" gpurun_out/r2_split3.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-echo "== fixed ring ON (new launch plan)" > gpurun_out/r2_mid2.log; SCG_SPLIT_G=0 timeout 600 python /dev/stdin >> gpurun_out/r2_mid2.log 2>&1 <<'PY'
+echo "== fixed ring ON (new launch plan)" > gpurun_out/r2_mid3.log; SCG_SPLIT_G=0 timeout 600 python /dev/stdin >> gpurun_out/r2_mid3.log 2>&1 <<'PY'
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 import gym_supplychain_b200 as gsc
@@ -26,4 +26,4 @@ for kw in (dict(nodes_per_echelon=[2,3,2,4], num_products=3, avg_leadtime=3, max
         print(kw, mode, "variant", env.scg_info.kernel_variant, "%.3f ms %.3e steps/s frac %.3f" % (ms, v, v * B / 1e9 / 6549.1), flush=True)
         del env, acts, obs, rew, done; torch.cuda.empty_cache()
 PY
-grep -v "^\[scg\]" gpurun_out/r2_mid2.log
+grep -v "^\[scg\]" gpurun_out/r2_mid3.log

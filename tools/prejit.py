@@ -61,7 +61,11 @@ def split_variant(job):
     else:
         os.environ["SCG_SPLIT_G"] = str(g)
     t0 = time.time()
-    info, k = presets.n_per_stage(nodes_per_echelon=shape)
+    extra_kw = {}
+    if isinstance(shape, tuple):                        # (nodes per echelon, products, lead time)
+        shape, P, L = shape
+        extra_kw = dict(num_products=P, avg_leadtime=L, max_leadtime=L)
+    info, k = presets.n_per_stage(nodes_per_echelon=shape, **extra_kw)
     ok = FlatSpec(info, **k).precompile(mode, in_kernel_actions=rand)
     os.environ.pop("SCG_SPLIT_G", None)
     return "%s G=%s" % (shape, g), mode, rand, ok, time.time() - t0
@@ -69,7 +73,8 @@ def split_variant(job):
 
 SPLIT = [([5, 4, 7, 10], m, r, None) for m in ("mixed", "fast_f32") for r in (False, True)] + \
         [(10, m, False, None) for m in ("mixed", "fast_f32")] + \
-        [([5, 4, 7, 10], "mixed", False, g) for g in (2, 8)] + [([5, 4, 7, 10], m, False, 0) for m in ("mixed", "fast_f32")]
+        [([5, 4, 7, 10], "mixed", False, g) for g in (2, 8)] + [([5, 4, 7, 10], m, False, 0) for m in ("mixed", "fast_f32")] + \
+        [(sh, m, False, None) for sh in (([6, 5, 9, 7], 2, 2), ([4, 6, 5, 8], 3, 2), ([7, 3, 6, 9], 2, 3)) for m in ("mixed", "fast_f32")]
 
 
 def main():
