@@ -21,7 +21,8 @@ ONE JSON line on stdout (rank 0):
   other_configs .. every other BASELINE.json config, measured in the same run: c1 (beergame-v0 single env), c2 (linear
                    65,536 envs: step API / CUDA graph / fused), c3 (2perstage 1M envs x 128), c4s (ntom STRONG scaling:
                    8,388,608 envs in total), c5 (beergame-v2 + supplychain-v0 16,777,216-env sweep, two handles per GPU)
-                   -- c4s and c5 at every N, the single-GPU configs at N=1 only.
+                   -- c4s and c5 at every N, the single-GPU configs at N=1 only; plus `large_chain_5_4_7_10`, the reference's
+                   26-node golden-return chain on the node-parallel split kernel (not a BASELINE config).
 """
 import argparse
 import json
@@ -767,6 +768,37 @@ def run_c1(ctx, args):
     return out
 
 
+def run_large_chain(ctx, args, mode, shape=(5, 4, 7, 10), n=1 << 18, T=32, iters=3):
+    """Not a BASELINE.json config: the reference's large golden-return chain (test_Nperstage.py:23-53) on the node-parallel
+    split kernel (several lanes per env, warp-shuffle sums; run-time instantiated), so that its number is in the line too."""
+    import gym_supplychain_b200 as gsc
+    torch = ctx.torch
+    env = gsc.make(ENV_ID, num_envs=n, mode=mode, seed=args.seed, auto_reset=True, device=ctx.dev, nodes_per_echelon=list(shape))
+    env.reset()
+    nA, nO = env.n_actions, env.n_obs
+    acts = torch.empty((T, n, nA), device=ctx.dev).uniform_(-1, 1)
+    obs = torch.empty((T, n, nO), device=ctx.dev); rew = torch.empty((T, n), device=ctx.dev)
+    done = torch.empty((T, n), dtype=torch.uint8, device=ctx.dev)
+    for _ in range(2):
+        env.rollout(T, acts, out=(obs, rew, done))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        env.rollout(T, acts, out=(obs, rew, done))
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    B = bytes_per_env_step(nA, nO)
+    peak, _ = measured_peak()
+    v = n * T / (ms * 1e-3)
+    out = {"workload": "SupplyChainNPerStage(%s), %d products (A=%d, O=%d), %d envs, fused %d-period rollout" % (list(shape), env.flat.P, nA, nO, n, T),
+           "mode": mode, "value": v, "unit": "env-steps/s", "ms_per_call": ms, "bytes_per_env_step": B, "roofline_frac": v * B / 1e9 / peak,
+           "kernel_variant": env.scg_info.kernel_variant, "kernel": "sc_split_rollout (node-parallel)" if env.scg_info.kernel_variant == 101 else "other",
+           "gpu_launches": iters + 2}
+    del env, acts, obs, rew, done
+    return out
+
+
 def compact(res, cfg, mode):
     return {"workload": workload_config(cfg, None, None, None, None)["workload"], "mode": mode, "value": res["value"],
             "unit": "env-steps/s", "envs_total": res["n_total"], "envs_per_gpu": res["n_local"], "periods_per_step": res["T_step"],
@@ -917,6 +949,7 @@ def run_ours(args):
                 guarded("c2", lambda: run_c2(ctx, args, mode, iters=4))
             if cfg != "c1":
                 guarded("c1", lambda: run_c1(ctx, args))
+            guarded("large_chain_5_4_7_10", lambda: {m: run_large_chain(ctx, args, m) for m in ("fast_f32", "mixed")})
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload, the reference itself, on the host cores ----
     cpu = None

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
 
         // one week of one env; `a_now` is the (pre-loaded) action row of the 4-level fast path
         long long io = env;                                            // running index of (week s, this env) in the [T, n] outputs
+        Philox4 blk = Philox4{0, 0, 0, 0}; unsigned blk_q = 0xFFFFFFFFu;   // cached random block of weeks 4q+1 .. 4q+4
         auto week_step = [&](int s, int4 a_now) {
             if (week >= sp.T) {                                        // finished, not auto-reset: frozen
                 write_obs(io); reward[io] = 0; done[io] = 1;
@@ -126,10 +127,17 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
             int dem, delay;
             const bool rnd_dem = INP == 0 ? (!inj_demand && sp.dem_hi > sp.dem_lo) : INP == 2;
             const bool rnd_del = INP == 0 ? (!inj_delays && sp.del_hi > sp.del_lo) : INP == 2;
-            Philox4 wk = Philox4{0, 0, 0, 0};
-            if (rnd_dem || rnd_del) wk = rng_block(key, genv, episode, (unsigned)week, STREAM_BG_DEMAND, 0);
+            // One Philox block feeds FOUR consecutive weeks of this (env, episode): block q = (week-1) >> 2, word (week-1) & 3,
+            // demand from the low 16 bits, delay from the high 16 (multiply-shift; bias < span / 65536).  The block is kept
+            // in registers and refilled every fourth week (a 37-byte env-week cannot afford ten Philox rounds per week).
+            unsigned wk = 0u;
+            if (rnd_dem || rnd_del) {
+                const unsigned q = (unsigned)(week - 1) >> 2;
+                if (q != blk_q) { blk = rng_block(key, genv, episode, q, STREAM_BG_DEMAND, 0); blk_q = q; }
+                wk = pick_word(blk, (week - 1) & 3);
+            }
             if (inj_demand) dem = inj_demand[(long long)(week - 1) * n + env];
-            else if (rnd_dem) dem = uniform_int(wk.x, sp.dem_lo, (unsigned)(sp.dem_hi - sp.dem_lo));
+            else if (rnd_dem) dem = sp.dem_lo + (int)(((wk & 0xFFFFu) * (unsigned)(sp.dem_hi - sp.dem_lo)) >> 16);
             else dem = s_dem[week - 1];
             if (inj_delays) {
                 delay = inj_delays[(long long)(week - 1) * n + env];
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                     delay = delay < 0 ? 0 : RING;
                 }
             }
-            else if (rnd_del) delay = uniform_int(wk.y, sp.del_lo, (unsigned)(sp.del_hi - sp.del_lo));
+            else if (rnd_del) delay = sp.del_lo + (int)(((wk >> 16) * (unsigned)(sp.del_hi - sp.del_lo)) >> 16);
             else delay = s_del[week - 1];
             // 2. fill orders (:79-89)
             int incoming[LMAX], fill[LMAX], deliver[LMAX];
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
             const bool fin = (week == sp.T);
             if (fin) {
                 rs.add(ep_ret);
-                if (auto_reset) { ++episode; week = 0; ep_ret = 0.0; do_reset_state(); }
+                if (auto_reset) { ++episode; week = 0; ep_ret = 0.0; blk_q = 0xFFFFFFFFu; do_reset_state(); }
             }
             write_obs(io);
             reward[io] = r;

@@ -290,10 +290,11 @@ def _philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def test_beergame_in_kernel_generators_are_the_documented_philox_streams():
-    """beergame-v2 with randint demand / delays (beergame2_env.py:86-92, hi exclusive) generated IN the kernel: demand and
-    delay of (env, episode, week) are words x and y of the Philox block keyed (seed, global env, episode, week, stream 4),
-    mapped by multiply-shift.  The tables rebuilt on the host with that rule drive the C oracle to the same trajectories,
-    over two episodes with auto-reset and a non-zero first_env."""
+    """beergame-v2 with randint demand / delays (beergame2_env.py:86-92, hi exclusive) generated IN the kernel: ONE Philox
+    block keyed (seed, global env, episode, q, stream 4) feeds the four weeks 4q+1 .. 4q+4 of an env -- week w takes word
+    (w-1) & 3, demand from its low 16 bits and delay from its high 16 bits, mapped by multiply-shift.  The tables rebuilt on
+    the host with that rule drive the C oracle to the same trajectories, over two episodes with auto-reset and a non-zero
+    first_env."""
     from oracle.c_oracle import CBeerGameOracle
     n, T, seed, first = 257, 35, 0x1234567890ABCDEF, 1000
     env = gsc.BeerGameEnv2(customer_demand=(0, 16), shipment_delays=(0, 5), num_envs=n, seed=seed, auto_reset=True, first_env=first)
@@ -308,10 +309,14 @@ def test_beergame_in_kernel_generators_are_the_documented_philox_streams():
         for w in range(1, T + 1):
             c1 = ((genv >> np.uint64(32)) & np.uint64(0xFFFF)) | np.uint64(4 << 28)          # block 0, stream STREAM_BG_DEMAND = 4
             # episode counter: creating the handle resets once (episode 0), env.reset() above started episode 1
-            x, y, _, _ = _philox4x32_10(genv, c1, np.full(n, ep + 1, np.uint64), np.full(n, w, np.uint64), seed & 0xFFFFFFFF, seed >> 32)
-            dem[:, w - 1] = (x * np.uint64(16)) >> np.uint64(32)                               # lo + umulhi(word, hi - lo)
-            dl[:, w - 1] = (y * np.uint64(5)) >> np.uint64(32)
+            words = _philox4x32_10(genv, c1, np.full(n, ep + 1, np.uint64), np.full(n, (w - 1) >> 2, np.uint64), seed & 0xFFFFFFFF, seed >> 32)
+            word = words[(w - 1) & 3]
+            dem[:, w - 1] = ((word & np.uint64(0xFFFF)) * np.uint64(16)) >> np.uint64(16)      # lo + (field * (hi - lo)) >> 16
+            dl[:, w - 1] = ((word >> np.uint64(16)) * np.uint64(5)) >> np.uint64(16)
         assert dem.min() == 0 and dem.max() == 15 and dl.min() == 0 and dl.max() == 4
+        for vals, k in ((dem, 16), (dl, 5)):                   # randint(lo, hi): every value equally likely (5 sigma)
+            cnt = np.bincount(vals.ravel(), minlength=k)
+            assert np.abs(cnt - vals.size / k).max() < 5 * np.sqrt(vals.size / k)
         for e in range(0, n, 5):
             ora.reset(dem[e], dl[e])
             for t in range(T):

@@ -244,3 +244,19 @@ def test_instantiated_kernels_keep_the_env_state_in_registers(tmp_path, monkeypa
     assert m, out[-400:]
     regs, stack = int(m.group(1)), int(m.group(2))
     assert stack <= 700, "kernel state demoted to local memory? REG %d STACK %d" % (regs, stack)
+
+
+def test_bench_config_tables():
+    """bench.py's host-side bookkeeping: the strong-scaling shape of configs[3] always covers 8,388,608 envs x 128 periods,
+    the algorithmic bytes follow SURVEY 8(d), the mixed CPU rate is the harmonic combination, every config is named."""
+    import bench
+    for world in (1, 2, 4, 8):
+        n_local, T_launch, lps = bench.c4s_shape(world)
+        assert n_local * world == 1 << 23 and T_launch * lps == 128 and T_launch >= 16
+        assert n_local * T_launch * bench.BYTES_PER_ENV_STEP <= 80e9          # I/O buffers of one launch fit a 180 GB GPU
+    assert bench.BYTES_PER_ENV_STEP == 561 and bench.bytes_per_env_step(14, 27) == 169 and bench.bytes_per_env_step(4, 14) == 77
+    assert abs(bench.mixed_rate([(100.0, 720.0), (1000.0, 700.0)]) - 1420.0 / (7.2 + 0.7)) < 1e-9
+    for cfg in ("c1", "c2", "c3", "c4", "c4s", "c5"):
+        c = bench.workload_config(cfg, 1, 1, 1, "mixed")
+        assert c["id"] == cfg and "obs_mode" in c and cfg in bench.REF_SAMPLE
+    assert set(case for v in bench.REF_SAMPLE.values() for case, _, _ in v) <= set(bench.REF_CASES)
