@@ -82,5 +82,5 @@ def build(force=False, verbose=False, defines=(), tag=None):
 
 if __name__ == "__main__":
     tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), None)
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=[a for a in sys.argv if a.startswith("-D")], tag=tag)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=[a for a in sys.argv if a.startswith("-D") or a.startswith("--ptxas-options")], tag=tag)
     print(path)

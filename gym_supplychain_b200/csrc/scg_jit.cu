@@ -507,7 +507,8 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     while (warps > 1 && (size_t)warps * tile > budget) warps >>= 1;
     if (tile > budget) return false;                                                       // one warp tile must fit shared memory
     j.threads = 32 * warps;
-    j.smem = 128 + (size_t)warps * tile;
+    const size_t hdr = 128 + (hs.stochL ? ((size_t)j.ML * j.ML * (f64 ? 8 : 4) + 127) / 128 * 128 : 0);     // layered_smem_header
+    j.smem = hdr + (size_t)warps * tile;
     const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024)), by_regs = 65536 / (j.threads * regs);
     const int minb = by_smem < by_regs ? by_smem : by_regs;
     j.minb = minb < 1 ? 1 : (minb > 16 ? 16 : minb);

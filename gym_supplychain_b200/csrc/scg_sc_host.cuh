@@ -17,7 +17,7 @@ static inline std::vector<unsigned long long> sc_leadtime_thresholds(const ScHos
     double p = std::exp(-lam), F = p;
     for (int j = 0; j + 1 < hs.maxL; ++j) {
         const double x = std::ceil(F * 4294967296.0);
-        thr[j] = x >= 4294967296.0 ? (1ull << 32) : (unsigned long long)x;      // 2^32: never reached by a 32-bit word
+        thr[j] = x >= 4294967296.0 ? (1ull << 32) : (x < 1.0 ? 1ull : (unsigned long long)x);   // 2^32: never reached by a 32-bit word
         p *= lam / (double)(j + 1);
         F += p;
     }
@@ -211,7 +211,7 @@ static int sc_launch_layered(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
-    const size_t smem = 128 + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
+    const size_t smem = layered_smem_header<Real, ML, STOCH>() + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
     static unsigned long long attr_set[2] = {0ull, 0ull};         // [random actions?] bit d: shared-memory size set on device d

@@ -251,6 +251,7 @@ struct RingRegs {
     static constexpr bool kFixed = false;
     Real stock[NP];
     Real slot[NP * L];
+    const Real* onehot = nullptr;          // STOCH: L x L identity in shared memory, row lt-1 = where a lead time lt lands
     __device__ __forceinline__ RingRegs(const Real*, const Real*) {}
     __device__ __forceinline__ void commit() {}
     __device__ __forceinline__ void load_slot(int i, Real v) { slot[i] = v; }
@@ -269,8 +270,11 @@ struct RingRegs {
     __device__ __forceinline__ void push(int np, int, int lt, Real amount) {
         if constexpr (!STOCH) slot[np * L + L - 1] += amount;              // constant lead time == ring depth
         else {
+            // data-dependent slot: one vector load of the one-hot row and an FMA per slot (amount * 1 or amount * 0 -- the same
+            // values as a compare and a select per slot, a third of the instructions; amounts are finite)
+            const Real* row = onehot + (lt - 1) * L;
 #pragma unroll
-            for (int k = 0; k < L; ++k) slot[np * L + k] += (lt - 1 == k) ? amount : (Real)0;
+            for (int k = 0; k < L; ++k) slot[np * L + k] = fma(amount, row[k], slot[np * L + k]);
         }
     }
     __device__ __forceinline__ void push_own(int np, int t, int lt, Real amount) { push(np, t, lt, amount); }
@@ -451,6 +455,12 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
 
+// Bytes in front of the per-warp tiles: the mbarriers and, for stochastic lead times, the one-hot table of RingRegs::push.
+template <class Real, int ML, bool STOCH>
+__host__ __device__ constexpr int layered_smem_header() {
+    return 128 + (STOCH ? (ML * ML * (int)sizeof(Real) + 127) / 128 * 128 : 0);
+}
+
 // ---------------------------------------------------------------------------------
 // the fused rollout kernel
 // ---------------------------------------------------------------------------------
@@ -476,7 +486,9 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // smem: [one mbarrier per warp, padded to 128 B][per warp: action tile | obs tile]
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
-    Io* s_act = reinterpret_cast<Io*>(smem_raw + 128) + (size_t)warp * 32 * (A + O);
+    // [128 B: one mbarrier per warp][STOCH: ML x ML one-hot table of Real, padded to 128 B][per warp: action tile | obs tile]
+    constexpr int kHdr = layered_smem_header<Real, ML, STOCH>();
+    Io* s_act = reinterpret_cast<Io*>(smem_raw + kHdr) + (size_t)warp * 32 * (A + O);
     Io* s_obs = s_act + 32 * A;
     const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * 32;
     const long long env = env0 + lane;
@@ -502,6 +514,12 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     constexpr bool kFixed = (SCG_FIXED_RING != 0) && sizeof(Real) == 8 && sizeof(Io) == 4 && !STOCH;
     using Pp = typename PipeChoice<kFixed, Real, NP, ML, STOCH>::type;
     Pp pp(c.q_scale, c.q_inv);
+    if constexpr (STOCH) {
+        Real* tab = reinterpret_cast<Real*>(smem_raw + 128);
+        for (int i = threadIdx.x; i < ML * ML; i += THREADS) tab[i] = (i / ML == i % ML) ? (Real)1 : (Real)0;
+        __syncthreads();
+        pp.onehot = tab;
+    }
     RegDemand<RP> dm;
     int t = 0; unsigned episode = 0; double ep_ret = 0.0;
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
