@@ -209,7 +209,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, None, None, None, None),
+            "config": full_config(cfg, args, int(os.environ.get("WORLD_SIZE", "1"))),
             "arm": "the unmodified reference (baseline/_ref, pip-installed from /root/reference) through the gym stand-in, its own "
                    "reset()/step() loop with a pre-sampled random policy, one process per host core",
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "cpu": cpu_model(), "kind": "reference", "sample": sample},
@@ -338,6 +338,34 @@ def workload_config(cfg, n_local, n_total, T, mode):
                               "time-sorted, SURVEY F3 -- only mode exact_f64 reproduces the heap-layout quirk)",
                   "auto_reset": True})
     return c
+
+
+CONFIG_SHAPES = {"c3": (14, 27), "c4": (60, 79), "c4s": (60, 79)}     # (A, O) of the rollout configs
+
+
+def full_config(cfg, args, world):
+    """The `config` object of the JSON line, computed from the command line alone so that BOTH arms print the same one."""
+    mode = args.mode
+    if cfg in CONFIG_SHAPES:
+        nA, nO = CONFIG_SHAPES[cfg]
+        if cfg == "c4s":
+            n_local, T_launch, lps = c4s_shape(world)
+        else:
+            n_local, T_launch, lps = args.envs_per_gpu, args.rollout_T, 1
+        B = bytes_per_env_step(nA, nO)
+        return dict(workload_config(cfg, n_local, n_local * world, T_launch * lps, mode), bytes_per_env_step=B, periods_per_launch=T_launch,
+                    l2="inputs+outputs per launch are %.1f GB per GPU (> 126 MB L2): no flush needed" % (n_local * T_launch * B / 1e9),
+                    collective=("one all-gather of the 5 episode-return statistics (40 B per rank) per step (NCCL), issued "
+                                "async after the rollout and consumed one step late: overlapped with the next rollout")
+                    if world > 1 else "none (1 GPU)")
+    if cfg == "c2":
+        return dict(workload_config("c2", 65536, 65536, 360, mode),
+                    l2="fused rollout: 1.8 GB per call (> L2); the step API's 5 MB per step lives in L2 (reported as such)")
+    if cfg == "c5":
+        per_family = (1 << 24) // 2 // world
+        return dict(workload_config("c5", per_family, 1 << 24, None, mode),
+                    l2="every launch streams more than 2 GB per GPU (> 126 MB L2): no flush needed")
+    return workload_config("c1", 1, 1, 35, None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -878,13 +906,7 @@ def run_ours(args):
                 "scaling": "strong" if cfg == "c4s" else "weak", "vs_baseline": None,
                 "dtype": "f32" if mode == "fast_f32" else "f32 I/O; f64 stocks and arithmetic, in-transit amounts as 32-bit fixed point",
                 "data": "synthetic",
-                "config": dict(workload_config(cfg, n_local, m["n_total"], m["T_step"], mode),
-                               bytes_per_env_step=m["bytes_per_env_step"], periods_per_launch=T_launch,
-                               l2="inputs+outputs per launch are %.1f GB per GPU (> 126 MB L2): no flush needed"
-                                  % (n_local * T_launch * m["bytes_per_env_step"] / 1e9),
-                               collective=("one all-gather of the 5 episode-return statistics (40 B per rank) per step (NCCL), issued "
-                                           "async after the rollout and consumed one step late: overlapped with the next rollout")
-                               if world > 1 else "none (1 GPU)"),
+                "config": full_config(cfg, args, world),
                 "clocks": m["clocks"], "e2e": e2e, "gpu_launches": m["launches"],
                 "roofline": {"bound": "hbm", "achieved": m["achieved_gbs"], "peak": m["peak"], "unit": "GB/s", "frac": m["frac"],
                              "traffic": traffic, "traffic_source": ("measured_offline: ncu --set full capture of this command, " + traffic_src)
@@ -898,8 +920,7 @@ def run_ours(args):
         f = r["fused_360_period_rollout"]
         line = {"metric": "env_steps_per_sec", "value": r["value"], "unit": "env-steps/s", "n_gpus": world, "steps": 6, "warmup": 3,
                 "ms_per_step": f["ms_per_call"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 I/O; f64 stocks", "data": "synthetic", "config": dict(workload_config("c2", 65536, 65536, 360, mode),
-                                                                                   l2="fused rollout: 1.8 GB per call (> L2); the step API's 5 MB per step lives in L2 (reported as such)"),
+                "dtype": "f32 I/O; f64 stocks", "data": "synthetic", "config": full_config("c2", args, world),
                 "clocks": None, "gpu_launches": r["gpu_launches"], "variants": r,
                 "roofline": {"bound": "hbm", "achieved": f["roofline_frac"] * peak, "peak": peak, "unit": "GB/s", "frac": f["roofline_frac"],
                              "traffic": None, "kernel": kernel_name("supplychain-linear-v0", mode), "kernel_ms": f["ms_per_call"], "peak_source": peak_src},
@@ -909,7 +930,7 @@ def run_ours(args):
         line = {"metric": "env_steps_per_sec", "value": r["value"], "unit": "env-steps/s", "n_gpus": world, "steps": 1, "warmup": 1,
                 "ms_per_step": r["ms_per_sweep"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int32 (beer game) / f32 I/O, f64 state (supply chain)", "data": "synthetic",
-                "config": dict(workload_config("c5", r["envs_per_gpu_per_family"], r["envs_total"], None, mode)), "clocks": None,
+                "config": full_config("c5", args, world), "clocks": None,
                 "gpu_launches": r["gpu_launches"], "detail": r,
                 "roofline": {"bound": "hbm", "frac": r["roofline_frac"], "unit": "GB/s", "traffic": None,
                              "kernel": "bg_kernel<4,4,1> + " + kernel_name("supplychain-v0", mode)}, "e2e": None}
@@ -917,7 +938,7 @@ def run_ours(args):
         r = run_c1(ctx, args)
         line = {"metric": "env_steps_per_sec", "value": r["value"], "unit": "env-steps/s", "n_gpus": 1, "steps": 20, "warmup": 1,
                 "ms_per_step": r["us_per_step"] * 35e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-                "data": "synthetic", "config": workload_config("c1", 1, 1, 35, None), "clocks": None, "gpu_launches": r["gpu_launches"],
+                "data": "synthetic", "config": full_config("c1", args, 1), "clocks": None, "gpu_launches": r["gpu_launches"],
                 "detail": r, "roofline": None, "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 16,
                                                        "d2h_bytes_per_step": 21, "api": "scg_step_host (numpy in / numpy out)"}}
 
@@ -1003,11 +1024,7 @@ def emit_line(line):
     (_JSON_OUT or sys.stdout).flush()
 
 
-def main():
-    global _JSON_OUT
-    sys.stdout.flush()
-    _JSON_OUT = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)                                   # fd 1 -> stderr for the rest of the process (and its children)
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -1024,8 +1041,17 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--mode", default="mixed", choices=["fast_f32", "mixed"])
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary measurement of the other fp32-I/O mode")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    return args
+
+
+def main():
+    global _JSON_OUT
+    args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                   # fd 1 -> stderr for the rest of the process (and its children)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -77,6 +77,10 @@ def test_bench_reference_arm_under_torchrun_prints_once():
         return
     assert d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "env-steps/s" and d["config"]["id"] == "c4"
+    # the `config` object is the one our arm prints for the same command line (the driver compares them)
+    import bench
+    want = bench.full_config("c4", bench.parse_args(["--gpus", "2", "--rollout-T", "8"]), 2)
+    assert d["config"] == json.loads(json.dumps(want))
 
 
 def test_reference_install_is_the_unmodified_reference():

@@ -260,3 +260,10 @@ def test_bench_config_tables():
         c = bench.workload_config(cfg, 1, 1, 1, "mixed")
         assert c["id"] == cfg and "obs_mode" in c and cfg in bench.REF_SAMPLE
     assert set(case for v in bench.REF_SAMPLE.values() for case, _, _ in v) <= set(bench.REF_CASES)
+    # both arms print the same `config` object: it is a function of the command line and the world size alone
+    args = bench.parse_args(["--gpus", "2"])
+    for cfg in ("c1", "c2", "c3", "c4", "c4s", "c5"):
+        c = bench.full_config(cfg, args, 2)
+        assert c["id"] == cfg and ("l2" in c or cfg == "c1")
+    c4 = bench.full_config("c4", args, 2)
+    assert c4["envs_total"] == 2 * c4["envs_per_gpu"] and c4["bytes_per_env_step"] == 561 and "all-gather" in c4["collective"]
