@@ -77,8 +77,19 @@ bool load_nvrtc() {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_tried) return g_rtc.ok;
     g_tried = true;
-    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
-        g_rtc.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    // The CUDA toolkit's NVRTC by PATH first (SCG_NVRTC, $CUDA_HOME, /usr/local/cuda): a bare soname resolves to whatever copy
+    // the process has already loaded -- `import torch` preloads its bundled, older libnvrtc.so.12 -- and then the compiler
+    // (and with it the cache key below) would depend on the import order: a cache warmed by tools/prejit.py without torch
+    // was missed by every process that imported torch first.  The soname is the fallback for machines without a toolkit.
+    std::vector<std::string> names;
+    if (const char* e = getenv("SCG_NVRTC")) names.push_back(e);
+    for (const char* var : {"CUDA_HOME", "CUDA_PATH"})
+        if (const char* e = getenv(var)) names.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+    names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    names.push_back("libnvrtc.so.12");
+    names.push_back("libnvrtc.so");
+    for (const std::string& name : names) {
+        g_rtc.lib = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (g_rtc.lib) break;
     }
     if (g_rtc.lib) {
@@ -287,6 +298,7 @@ struct ScJit {
     bool failed = false;
     int S = 0, F = 0, W = 0, R = 0, ML = 0, threads = 0, minb = 0;
     int split_g = 0;           // > 0: the node-parallel kernel (scg_sc_split.cuh) with that many lanes per env
+    int act_tiles = 1;         // split kernel: action tiles per warp (2 = tile s+1 is copied during period s)
     bool baked = false;        // the spec's constants are compile-time constants of the instantiation (SCG_JIT_BAKE=1)
     size_t smem = 0;
     Packed consts;
@@ -342,8 +354,8 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     std::ostringstream src;
     std::string baked_inc;
     if (j.split_g > 0) {
-        snprintf(name, sizeof(name), "scg::sc_split_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %d, %d>", real, io, j.S, j.F, j.W, j.R,
-                 hs.P, hs.avgL, j.split_g, random_act ? "true" : "false", j.threads, j.minb);
+        snprintf(name, sizeof(name), "scg::sc_split_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %d, %d, %d>", real, io, j.S, j.F, j.W, j.R,
+                 hs.P, hs.avgL, j.split_g, random_act ? "true" : "false", j.threads, j.minb, j.act_tiles);
         src << "#include \"scg_sc_split.cuh\"\n";
     } else {
         snprintf(name, sizeof(name), "scg::sc_layered_rollout<%s, %s, %d, %d, %d, %d, %d, %d, %d, %s, %s, %d, %d>", real, io, j.S, j.F, j.W,
@@ -476,18 +488,28 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
         if (const char* e = getenv("SCG_SPLIT_G")) g = atoi(e);
         if (g == 2 || g == 4 || g == 8) {
             j.split_g = g;
-            const size_t wtile = (size_t)(32 / g) * (hs.A + hs.O) * es, budget_s = (size_t)227 * 1024 - 128 - 1024;
-            int warps = 4;
-            if (const char* e = getenv("SCG_SPLIT_WARPS")) warps = atoi(e) > 0 ? atoi(e) : 4;
+            size_t wtile = (size_t)(32 / g) * (hs.A + hs.O) * es;
+            const size_t budget_s = (size_t)227 * 1024 - 128 - 1024;
+            // fp64 state: one-warp blocks (bulk-copy addresses in uniform registers, +3 % measured); fp32: no difference, 4 warps
+            int warps = f64 ? 1 : 4;
+            if (const char* e = getenv("SCG_SPLIT_WARPS")) warps = atoi(e) > 0 ? atoi(e) : warps;
             while (warps > 1 && (size_t)warps * wtile > budget_s / 2) warps >>= 1;
             if (wtile <= budget_s) {
                 j.threads = 32 * warps;
-                j.smem = 128 + (size_t)warps * wtile;
                 // fp64 state with 4 or fewer lanes per env needs the whole register file (255 per thread); else 168
-                const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024)), by_regs = 65536 / (j.threads * ((f64 && g <= 4) ? 255 : 168));
+                const int by_regs = 65536 / (j.threads * ((f64 && g <= 4) ? 255 : 168));
+                // a second action tile per warp (the copy of tile s+1 overlaps period s, no L2 prefetch) where the register
+                // budget, not shared memory, still decides the occupancy
+                const size_t wtile2 = wtile + (size_t)(32 / g) * hs.A * es;
+                int tiles = (f64 && (int)(((size_t)227 * 1024) / (128 + (size_t)warps * wtile2 + 1024)) >= by_regs) ? 2 : 1;
+                if (const char* e = getenv("SCG_SPLIT_TILES")) tiles = atoi(e) == 2 ? 2 : 1;
+                j.act_tiles = tiles;
+                if (tiles == 2) wtile = wtile2;
+                j.smem = 128 + (size_t)warps * wtile;
+                const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024));
                 int minb = by_smem < by_regs ? by_smem : by_regs;
                 if (const char* e = getenv("SCG_SPLIT_MINB")) minb = atoi(e);
-                j.minb = minb < 1 ? 1 : (minb > 16 ? 16 : minb);
+                j.minb = minb < 1 ? 1 : (minb > 32 ? 32 : minb);
                 return true;
             }
             j.split_g = 0;
@@ -495,7 +517,8 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     }
     if (const char* e = getenv("SCG_JIT_BAKE")) j.baked = e[0] == '1' && j.consts.finite;
     // the whole state should stay in registers; the warp tiles must fit shared memory
-    const size_t tile = (size_t)32 * (hs.A + hs.O) * es, budget = (size_t)227 * 1024 - 128 - 1024;
+    const int act_tiles = (f64 && es == 4 && np_all >= 8) ? layered_action_tiles<double, float, 8>() : 1;    // same rule as the kernel
+    const size_t tile = (size_t)32 * (act_tiles * hs.A + hs.O) * es, budget = (size_t)227 * 1024 - 128 - 1024;
     // state registers: fp32 stocks + ring; fp64 stocks + 32-bit fixed-point ring (mixed, constant lead time); else all fp64
     const bool fixed_ring = f64 && es == 4 && !hs.stochL;
     const int state_regs = fixed_ring ? np_all * 2 + np_all * j.ML : np_all * (1 + j.ML) * (f64 ? 2 : 1);
@@ -503,7 +526,12 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     // an fp64-state kernel beyond 168 registers wants the whole file: it lives on instruction-level parallelism
     if (f64 && regs > 168) regs = 255;
     regs = regs < 64 ? 64 : (regs > 255 ? 255 : regs);
+    // Block size.  One-warp blocks keep every bulk-copy address in uniform registers and give the finest occupancy granularity;
+    // measured (profiles/r2_onewarp_blocks_ab_v2.log): +6..12 % with stochastic lead times, +16 % for an fp32 kernel beyond 168
+    // registers (4-4-4-4: 11 warps per SM instead of 10), -2 % where the kernel is already HBM-bound -> only in those two cases.
     int warps = regs > 168 ? 2 : 4;
+    if (hs.stochL || (!f64 && regs > 168)) warps = 1;
+    if (const char* e = getenv("SCG_JIT_WARPS")) warps = atoi(e) > 0 ? atoi(e) : warps;
     while (warps > 1 && (size_t)warps * tile > budget) warps >>= 1;
     if (tile > budget) return false;                                                       // one warp tile must fit shared memory
     j.threads = 32 * warps;
@@ -511,7 +539,7 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     j.smem = hdr + (size_t)warps * tile;
     const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024)), by_regs = 65536 / (j.threads * regs);
     const int minb = by_smem < by_regs ? by_smem : by_regs;
-    j.minb = minb < 1 ? 1 : (minb > 16 ? 16 : minb);
+    j.minb = minb < 1 ? 1 : (minb > 32 ? 32 : minb);
     return true;
 }
 

@@ -211,7 +211,8 @@ static int sc_launch_layered(const ScRun& r) {
     const ScDevSpec<Real>& sp = *reinterpret_cast<const ScDevSpec<Real>*>(r.dev_spec);
     const ScState<Real>& st = *reinterpret_cast<const ScState<Real>*>(r.state);
     ScInputs in{r.inj_demand, r.inj_leadtimes, r.key, r.first_env, r.auto_reset, r.err};
-    const size_t smem = layered_smem_header<Real, ML, STOCH>() + (size_t)(THREADS / 32) * 32 * (Tp::kA + Tp::kO) * sizeof(Io);
+    const size_t smem = layered_smem_header<Real, ML, STOCH>() +
+                        (size_t)(THREADS / 32) * 32 * (layered_action_tiles<Real, Io, Tp::kN * P>() * Tp::kA + Tp::kO) * sizeof(Io);
     const long long per_block = THREADS;
     const unsigned blocks = (unsigned)((st.n + per_block - 1) / per_block);
     static unsigned long long attr_set[2] = {0ull, 0ull};         // [random actions?] bit d: shared-memory size set on device d

@@ -216,7 +216,7 @@ __device__ __forceinline__ void split_fetch_demand(const ScDevSpec<Real>& sp, co
         }
 }
 
-template <class Real, class Io, int S, int F, int W, int R, int P, int L, int G, bool RANDOM_ACT, int THREADS, int MINB>
+template <class Real, class Io, int S, int F, int W, int R, int P, int L, int G, bool RANDOM_ACT, int THREADS, int MINB, int ACT_TILES = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
 sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps, const Io* __restrict__ actions, Io* __restrict__ obs,
                  Io* __restrict__ reward, unsigned char* __restrict__ done) {
@@ -232,11 +232,12 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
     using T2 = SplitTopo<Real, 2, S, F, W, R, P, L, G>;
     using T3 = SplitTopo<Real, 3, S, F, W, R, P, L, G>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = THREADS == 32 ? 0 : (int)(threadIdx.x >> 5);   // one-warp blocks: uniform addresses
     const int q = lane % G, e_in_warp = lane / G;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
-    Io* s_act = reinterpret_cast<Io*>(smem_raw + 128) + (size_t)warp * EPW * (A + O);
-    Io* s_obs = s_act + EPW * A;
+    static_assert(ACT_TILES == 1 || ACT_TILES == 2, "action tiles per warp");
+    Io* s_act0 = reinterpret_cast<Io*>(smem_raw + 128) + (size_t)warp * EPW * (ACT_TILES * A + O);
+    Io* s_obs = s_act0 + ACT_TILES * EPW * A;
     const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * EPW;
     const long long env = env0 + e_in_warp;
     const long long n = st.n;
@@ -248,7 +249,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
     const bool bulk_in = !RANDOM_ACT && n_here > 0 && (((size_t)actions) & 15) == 0 && (((size_t)n * A * 4) & 15) == 0 &&
                          (act_bytes & 15) == 0 && ((EPW * A * 4) & 15) == 0;
     const bool bulk_out = obs != nullptr && n_here > 0 && (((size_t)obs) & 15) == 0 && (((size_t)n * O * 4) & 15) == 0 &&
-                          (obs_bytes & 15) == 0 && ((EPW * (A + O) * 4) & 15) == 0;
+                          (obs_bytes & 15) == 0 && ((EPW * (ACT_TILES * A + O) * 4) & 15) == 0;
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
 
@@ -275,7 +276,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 
     if (bulk_in && n_steps > 0 && lane == 0) {
         mbar_expect_tx(bar, act_bytes);
-        bulk_g2s(s_act, actions + env0 * A, act_bytes, bar);
+        bulk_g2s(s_act0, actions + env0 * A, act_bytes, bar);
     }
     if (active) { t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env]; }
     split_load_state<Real, S, F, W, R, P, L, G, false>(sp, st, rg, q, n, env, active);
@@ -292,9 +293,19 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 #if SCG_SYNC_PERIOD
         __syncthreads();                   // keep the block's warps in the same stretch of the (larger than I-cache) loop body
 #endif
+        Io* s_act = s_act0 + ((ACT_TILES == 2 && bulk_in) ? (s & 1) * EPW * A : 0);
         if (bulk_in) {
-            if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
-            while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+            if constexpr (ACT_TILES == 1) {
+                if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
+                while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+            } else {
+                // two tiles: request tile s+1 into the buffer every lane finished reading in period s-1 (warp barriers below)
+                while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+                if (lane == 0 && s + 1 < n_steps) {
+                    mbar_expect_tx(bar, act_bytes);
+                    bulk_g2s(s_act0 + ((s + 1) & 1) * EPW * A, actions + (io0 + n) * A, act_bytes, bar);
+                }
+            }
         } else if (!RANDOM_ACT && n_here > 0) {
             __syncwarp();
             warp_copy<Io>(s_act, actions + io0 * A, n_here * A, lane);
@@ -374,7 +385,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
             }
         }
         __syncwarp();                      // every lane is done with the action tile of period s
-        if (bulk_in && s + 1 < n_steps && lane == 0) {
+        if (ACT_TILES == 1 && bulk_in && s + 1 < n_steps && lane == 0) {
             mbar_expect_tx(bar, act_bytes);
             bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
         }

@@ -455,6 +455,20 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
 
+// Action tiles per warp.  The fp64-state kernels with fp32 I/O are register-bound at 8-12 warps per SM, which leaves shared
+// memory for TWO action tiles: the bulk copy of tile s+1 is issued at the top of period s, a whole period ahead, instead of
+// after the step with an L2 prefetch to hide its latency (the prefetch instruction alone held the warp for 2.8 % of the
+// headline kernel's time, profiles/r2_ncu_ntom_mixed_v12_summary.txt).  SCG_DBUF_ACTIONS=0 builds the single-tile form.
+#ifndef SCG_DBUF_ACTIONS
+#define SCG_DBUF_ACTIONS 1
+#endif
+// Interleaved A/B (profiles/r2_action_tile_double_buffer_ab.log): ntom +3.1 %, supplychain-v0 +1.8 %, 2-2-2-2 with two
+// products +1 %; the chains with tiny tiles lose (linear -8 %, 1-1-1-3 -1 %), hence the bound on the (node, product) count.
+template <class Real, class Io, int NP>
+__host__ __device__ constexpr int layered_action_tiles() {
+    return (SCG_DBUF_ACTIONS != 0 && sizeof(Real) == 8 && sizeof(Io) == 4 && NP >= 8) ? 2 : 1;
+}
+
 // Bytes in front of the per-warp tiles: the mbarriers and, for stochastic lead times, the one-hot table of RingRegs::push.
 template <class Real, int ML, bool STOCH>
 __host__ __device__ constexpr int layered_smem_header() {
@@ -483,13 +497,16 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     constexpr int K = Tp::kK;
     constexpr int N = Tp::kN, NP = N * P, A = Tp::kA, O = Tp::kO, RP = Tp::kRP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // one warp per block: every tile / barrier / bulk-copy address derives from blockIdx alone, so the compiler keeps it in
+    // uniform registers (a warp index read from threadIdx costs a register-to-uniform loop around every bulk copy)
+    const int lane = threadIdx.x & 31, warp = THREADS == 32 ? 0 : (int)(threadIdx.x >> 5);
     // smem: [one mbarrier per warp, padded to 128 B][per warp: action tile | obs tile]
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
     // [128 B: one mbarrier per warp][STOCH: ML x ML one-hot table of Real, padded to 128 B][per warp: action tile | obs tile]
     constexpr int kHdr = layered_smem_header<Real, ML, STOCH>();
-    Io* s_act = reinterpret_cast<Io*>(smem_raw + kHdr) + (size_t)warp * 32 * (A + O);
-    Io* s_obs = s_act + 32 * A;
+    constexpr int kActTiles = layered_action_tiles<Real, Io, NP>();
+    Io* s_act0 = reinterpret_cast<Io*>(smem_raw + kHdr) + (size_t)warp * 32 * (kActTiles * A + O);
+    Io* s_obs = s_act0 + kActTiles * 32 * A;
     const long long env0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * 32;
     const long long env = env0 + lane;
     const long long n = st.n;
@@ -544,7 +561,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     // prologue: start moving the first action tile while the state is being loaded
     if (bulk_in && n_steps > 0 && lane == 0) {
         mbar_expect_tx(bar, act_bytes);
-        bulk_g2s(s_act, actions + env0 * A, act_bytes, bar);
+        bulk_g2s(s_act0, actions + env0 * A, act_bytes, bar);
     }
     if (active) {
         t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env];
@@ -561,10 +578,21 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 #if SCG_SYNC_PERIOD
         __syncthreads();                   // keep the block's warps in the same stretch of the (larger than I-cache) loop body
 #endif
+        Io* s_act = s_act0 + ((kActTiles == 2 && bulk_in) ? (s & 1) * 32 * A : 0);
         if (bulk_in) {
-            // tile s was requested one period ago (or in the prologue); ask L2 for tile s+1 now
-            if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
-            while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+            // tile s was requested one period ago (or in the prologue)
+            if constexpr (kActTiles == 1) {
+                if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);     // ask L2 for tile s+1 now
+                while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+            } else {
+                while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
+                // request tile s+1 into the other buffer: every lane finished reading it in period s-1 (a warp barrier
+                // separates the periods, below)
+                if (lane == 0 && s + 1 < n_steps) {
+                    mbar_expect_tx(bar, act_bytes);
+                    bulk_g2s(s_act0 + ((s + 1) & 1) * 32 * A, actions + (io0 + n) * A, act_bytes, bar);
+                }
+            }
         } else if (!RANDOM_ACT && n_here > 0) {
             __syncwarp();
             warp_copy<Io>(s_act, actions + io0 * A, n_here * A, lane);
@@ -625,11 +653,15 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                 }
             }
         }
-        __syncwarp();                      // every lane is done with the action tile of period s
-        if (bulk_in && s + 1 < n_steps && lane == 0) {
-            // request tile s+1 now: it lands while the observation below is computed and stored
-            mbar_expect_tx(bar, act_bytes);
-            bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
+        if constexpr (kActTiles == 1) {
+            __syncwarp();                      // every lane is done with the action tile of period s
+            if (bulk_in && s + 1 < n_steps && lane == 0) {
+                // request tile s+1 now: it lands while the observation below is computed and stored
+                mbar_expect_tx(bar, act_bytes);
+                bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
+            }
+        } else if (bulk_in && !bulk_out && obs == nullptr) {
+            __syncwarp();                      // no observation output: nothing else separates the periods' tile reads
         }
         if (bulk_out) {
             if (lane == 0) bulk_wait_read_all();   // the previous obs tile has left shared memory

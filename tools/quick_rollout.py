@@ -18,11 +18,12 @@ try:
     PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-SIZES = {"ntom": (1 << 20, 128), "2perstage": (1 << 20, 128), "linear": (1 << 22, 128), "oneonen": (1 << 21, 128)}
+SIZES = {"ntom": (1 << 20, 128), "2perstage": (1 << 20, 128), "linear": (1 << 22, 128), "oneonen": (1 << 21, 128), "v0": (1 << 20, 128), "multiproduct": (1 << 20, 128)}
+IDS = {"v0": "supplychain-v0", "multiproduct": "sc-2perstage-multiproduct-v0"}
 for case in args.cases.split(","):
     name, mode = case.split(":")
     n, T = SIZES[name]
-    env = gsc.make("supplychain-%s-v0" % name, num_envs=n, mode=mode, seed=0, auto_reset=True)
+    env = gsc.make(IDS.get(name, "supplychain-%s-v0" % name), num_envs=n, mode=mode, seed=0, auto_reset=True)
     env.reset()
     A, O = env.n_actions, env.n_obs
     g = torch.Generator(device="cuda"); g.manual_seed(1)

@@ -34,6 +34,8 @@ for shape_s in args.shapes.split(";"):
         for cfg in args.configs.split(","):
             g, mb = cfg.split(":")
             os.environ["SCG_SPLIT_G"] = g
+            if g == "d":                                   # "d:0" = the planned lane count and launch shape
+                os.environ.pop("SCG_SPLIT_G")
             os.environ["SCG_SPLIT_MINB"] = mb
             if mb == "0":
                 os.environ.pop("SCG_SPLIT_MINB")
