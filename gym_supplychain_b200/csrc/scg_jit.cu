@@ -298,7 +298,8 @@ struct ScJit {
     bool failed = false;
     int S = 0, F = 0, W = 0, R = 0, ML = 0, threads = 0, minb = 0;
     int split_g = 0;           // > 0: the node-parallel kernel (scg_sc_split.cuh) with that many lanes per env
-    int act_tiles = 1;         // split kernel: action tiles per warp (2 = tile s+1 is copied during period s)
+    int act_tiles = 1;         // action tiles per warp (2 = tile s+1 is copied during period s)
+    bool one_tile_define = false;   // layered kernel: compile with -DSCG_DBUF_ACTIONS=0 (its own rule would take two tiles)
     bool baked = false;        // the spec's constants are compile-time constants of the instantiation (SCG_JIT_BAKE=1)
     size_t smem = 0;
     Packed consts;
@@ -376,6 +377,7 @@ static int jit_compile(const ScJit& j, const ScHostSpec& hs, int mode, bool rand
     const std::string dir = lib_dir(), csrc = dir + "/csrc";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-I" + csrc};
     if (mode == SCG_MODE_FAST_F64) opts.push_back("--fmad=false");      // same contract as scg_sc_f64.cu
+    if (j.split_g == 0 && j.one_tile_define) opts.push_back("-DSCG_DBUF_ACTIONS=0");
     if (const char* extra = getenv("SCG_JIT_DEFINES")) {                // kernel A/B experiments: "-DX=1 -DY=0"
         std::istringstream is(extra);
         for (std::string tok; is >> tok;) opts.push_back(tok);
@@ -517,8 +519,8 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     }
     if (const char* e = getenv("SCG_JIT_BAKE")) j.baked = e[0] == '1' && j.consts.finite;
     // the whole state should stay in registers; the warp tiles must fit shared memory
-    const int act_tiles = (f64 && es == 4 && np_all >= 8) ? layered_action_tiles<double, float, 8>() : 1;    // same rule as the kernel
-    const size_t tile = (size_t)32 * (act_tiles * hs.A + hs.O) * es, budget = (size_t)227 * 1024 - 128 - 1024;
+    size_t tile = (size_t)32 * (hs.A + hs.O) * es;
+    const size_t budget = (size_t)227 * 1024 - 128 - 1024;
     // state registers: fp32 stocks + ring; fp64 stocks + 32-bit fixed-point ring (mixed, constant lead time); else all fp64
     const bool fixed_ring = f64 && es == 4 && !hs.stochL;
     const int state_regs = fixed_ring ? np_all * 2 + np_all * j.ML : np_all * (1 + j.ML) * (f64 ? 2 : 1);
@@ -536,8 +538,17 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     if (tile > budget) return false;                                                       // one warp tile must fit shared memory
     j.threads = 32 * warps;
     const size_t hdr = 128 + (hs.stochL ? ((size_t)j.ML * j.ML * (f64 ? 8 : 4) + 127) / 128 * 128 : 0);     // layered_smem_header
+    const int by_regs = 65536 / (j.threads * regs);
+    // The kernel's own rule gives the fp64-state / fp32-I/O kernels a second action tile (layered_action_tiles).  Keep it only
+    // where registers, not shared memory, still decide the occupancy: 3-3-3-3 with 3 products dropped from 8 to 4 warps per SM
+    // and from 0.70 to 0.41 of the HBM peak with it (profiles/r2_midsize_chains_v4.log); otherwise compile with one tile.
+    const int rule_tiles = (f64 && es == 4) ? (np_all >= 8 ? layered_action_tiles<double, float, 8>() : 1) : 1;
+    const size_t tile2 = tile + (size_t)32 * hs.A * es;
+    j.act_tiles = (rule_tiles == 2 && (int)(((size_t)227 * 1024) / (hdr + (size_t)warps * tile2 + 1024)) >= by_regs) ? 2 : 1;
+    j.one_tile_define = rule_tiles == 2 && j.act_tiles == 1;
+    if (j.act_tiles == 2) tile = tile2;
     j.smem = hdr + (size_t)warps * tile;
-    const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024)), by_regs = 65536 / (j.threads * regs);
+    const int by_smem = (int)(((size_t)227 * 1024) / (j.smem + 1024));
     const int minb = by_smem < by_regs ? by_smem : by_regs;
     j.minb = minb < 1 ? 1 : (minb > 32 ? 32 : minb);
     return true;

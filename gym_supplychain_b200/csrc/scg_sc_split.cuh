@@ -296,12 +296,12 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
         Io* s_act = s_act0 + ((ACT_TILES == 2 && bulk_in) ? (s & 1) * EPW * A : 0);
         if (bulk_in) {
             if constexpr (ACT_TILES == 1) {
-                if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
+                if (s + 1 < n_steps && elect_one()) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);
                 while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
             } else {
                 // two tiles: request tile s+1 into the buffer every lane finished reading in period s-1 (warp barriers below)
                 while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
-                if (lane == 0 && s + 1 < n_steps) {
+                if (s + 1 < n_steps && elect_one()) {
                     mbar_expect_tx(bar, act_bytes);
                     bulk_g2s(s_act0 + ((s + 1) & 1) * EPW * A, actions + (io0 + n) * A, act_bytes, bar);
                 }
@@ -385,12 +385,12 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
             }
         }
         __syncwarp();                      // every lane is done with the action tile of period s
-        if (ACT_TILES == 1 && bulk_in && s + 1 < n_steps && lane == 0) {
+        if (ACT_TILES == 1 && bulk_in && s + 1 < n_steps && elect_one()) {
             mbar_expect_tx(bar, act_bytes);
             bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
         }
         if (bulk_out) {
-            if (lane == 0) bulk_wait_read_all();
+            bulk_wait_read_all();          // every lane: its own bulk groups (a no-op for the lanes that never issued one)
             __syncwarp();
         }
         if (active) {
@@ -433,14 +433,14 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
         if (bulk_out) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { bulk_s2g(obs + io0 * O, s_obs, obs_bytes); bulk_commit(); }
+            if (elect_one()) { bulk_s2g(obs + io0 * O, s_obs, obs_bytes); bulk_commit(); }
         } else if (obs != nullptr && n_here > 0) {
             __syncwarp();
             warp_copy<Io>(obs + io0 * O, s_obs, n_here * O, lane);
             __syncwarp();
         }
     }
-    if (bulk_out && lane == 0) bulk_wait_all();
+    if (bulk_out) bulk_wait_all();     // every lane: its own bulk groups
 
     if (active) {
         if (q == 0) { st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret; }

@@ -451,6 +451,13 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// One lane of a converged warp (elect.sync): the guard of the bulk-copy issue.  Unlike `lane == 0` the predicate is known to
+// the compiler as "exactly one lane", so it does not wrap the uniform-datapath copy instruction in a loop over the active lanes.
+__device__ __forceinline__ bool elect_one() {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
@@ -461,6 +468,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* g, unsigned bytes) 
 // headline kernel's time, profiles/r2_ncu_ntom_mixed_v12_summary.txt).  SCG_DBUF_ACTIONS=0 builds the single-tile form.
 #ifndef SCG_DBUF_ACTIONS
 #define SCG_DBUF_ACTIONS 1
+#endif
+#ifndef SCG_G2S_AT_TOP
+#define SCG_G2S_AT_TOP 0        // two action tiles: 1 = request tile s+1 at the top of period s; 0 = tile s+2 at its end, with the obs store
 #endif
 // Interleaved A/B (profiles/r2_action_tile_double_buffer_ab.log): ntom +3.1 %, supplychain-v0 +1.8 %, 2-2-2-2 with two
 // products +1 %; the chains with tiny tiles lose (linear -8 %, 1-1-1-3 -1 %), hence the bound on the (node, product) count.
@@ -501,7 +511,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     // uniform registers (a warp index read from threadIdx costs a register-to-uniform loop around every bulk copy)
     const int lane = threadIdx.x & 31, warp = THREADS == 32 ? 0 : (int)(threadIdx.x >> 5);
     // smem: [one mbarrier per warp, padded to 128 B][per warp: action tile | obs tile]
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp * 2;     // two per warp (one per action tile)
     // [128 B: one mbarrier per warp][STOCH: ML x ML one-hot table of Real, padded to 128 B][per warp: action tile | obs tile]
     constexpr int kHdr = layered_smem_header<Real, ML, STOCH>();
     constexpr int kActTiles = layered_action_tiles<Real, Io, NP>();
@@ -524,7 +534,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                          (((size_t)n * A * sizeof(Io)) & 15) == 0 && (act_bytes & 15) == 0 && ((32 * A * sizeof(Io)) & 15) == 0;
     const bool bulk_out = !SCG_NO_BULK && obs != nullptr && n_here > 0 && (((size_t)obs) & 15) == 0 && (((size_t)n * O * sizeof(Io)) & 15) == 0 &&
                           (obs_bytes & 15) == 0 && ((32 * (A + O) * sizeof(Io)) & 15) == 0;
-    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_mbar_init(); }
     __syncwarp();
 
     // fp64 state with fp32 I/O and a constant lead time: in-transit material as 32-bit fixed point (RingFixed)
@@ -562,6 +572,10 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     if (bulk_in && n_steps > 0 && lane == 0) {
         mbar_expect_tx(bar, act_bytes);
         bulk_g2s(s_act0, actions + env0 * A, act_bytes, bar);
+        if (kActTiles == 2 && !SCG_G2S_AT_TOP && n_steps > 1) {               // two tiles: tile s+2 is requested at the end of period s
+            mbar_expect_tx(bar + 1, act_bytes);
+            bulk_g2s(s_act0 + 32 * A, actions + (n + env0) * A, act_bytes, bar + 1);
+        }
     }
     if (active) {
         t = st.t[env]; episode = (unsigned)st.episode[env]; ep_ret = st.ep_ret[env];
@@ -582,16 +596,17 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
         if (bulk_in) {
             // tile s was requested one period ago (or in the prologue)
             if constexpr (kActTiles == 1) {
-                if (lane == 0 && s + 1 < n_steps) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);     // ask L2 for tile s+1 now
+                if (s + 1 < n_steps && elect_one()) bulk_prefetch_l2(actions + (io0 + n) * A, act_bytes);     // ask L2 for tile s+1 now
                 while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
             } else {
-                while (!mbar_try_wait(bar, (unsigned)(s & 1))) {}
-                // request tile s+1 into the other buffer: every lane finished reading it in period s-1 (a warp barrier
-                // separates the periods, below)
-                if (lane == 0 && s + 1 < n_steps) {
-                    mbar_expect_tx(bar, act_bytes);
-                    bulk_g2s(s_act0 + ((s + 1) & 1) * 32 * A, actions + (io0 + n) * A, act_bytes, bar);
+                // tile s sits in buffer s & 1 (requested two periods ago, at the end of period s-2, or in the prologue)
+                while (!mbar_try_wait(bar + (s & 1), (unsigned)((s >> 1) & 1))) {}
+#if SCG_G2S_AT_TOP
+                if (s + 1 < n_steps && elect_one()) {      // every lane finished reading that buffer in period s-1
+                    mbar_expect_tx(bar + ((s + 1) & 1), act_bytes);
+                    bulk_g2s(s_act0 + ((s + 1) & 1) * 32 * A, actions + (io0 + n) * A, act_bytes, bar + ((s + 1) & 1));
                 }
+#endif
             }
         } else if (!RANDOM_ACT && n_here > 0) {
             __syncwarp();
@@ -655,7 +670,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
         }
         if constexpr (kActTiles == 1) {
             __syncwarp();                      // every lane is done with the action tile of period s
-            if (bulk_in && s + 1 < n_steps && lane == 0) {
+            if (bulk_in && s + 1 < n_steps && elect_one()) {
                 // request tile s+1 now: it lands while the observation below is computed and stored
                 mbar_expect_tx(bar, act_bytes);
                 bulk_g2s(s_act, actions + (io0 + n) * A, act_bytes, bar);
@@ -664,7 +679,9 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
             __syncwarp();                      // no observation output: nothing else separates the periods' tile reads
         }
         if (bulk_out) {
-            if (lane == 0) bulk_wait_read_all();   // the previous obs tile has left shared memory
+            // the previous obs tile has left shared memory.  Every lane waits on its OWN bulk groups (a no-op for the lanes that
+            // never issued one): no divergent region around the wait
+            bulk_wait_read_all();
             __syncwarp();
         }
         if (active) {
@@ -713,17 +730,28 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
             reward[io0 + lane] = (Io)r;
             done[io0 + lane] = fin ? 1 : 0;
         }
+        const bool next_tile = kActTiles == 2 && !SCG_G2S_AT_TOP && bulk_in && s + 2 < n_steps;     // tile s+2 goes where tile s was
         if (bulk_out) {
             fence_proxy_async_smem();      // generic-proxy writes of the tile -> visible to the async proxy
             __syncwarp();
-            if (lane == 0) { bulk_s2g(obs + io0 * O, s_obs, obs_bytes); bulk_commit(); }
         } else if (obs != nullptr && n_here > 0) {
             __syncwarp();
             warp_copy<Io>(obs + io0 * O, s_obs, n_here * O, lane);
             __syncwarp();
         }
+        // ONE single-lane region per period issues both bulk copies: the obs tile of period s out, the action tile of period
+        // s+2 in (every lane is past the warp barriers above, i.e. done reading tile s)
+        if (bulk_out || next_tile) {
+            if (elect_one()) {
+                if (bulk_out) { bulk_s2g(obs + io0 * O, s_obs, obs_bytes); bulk_commit(); }
+                if (next_tile) {
+                    mbar_expect_tx(bar + (s & 1), act_bytes);
+                    bulk_g2s(s_act, actions + (io0 + 2 * n) * A, act_bytes, bar + (s & 1));
+                }
+            }
+        }
     }
-    if (bulk_out && lane == 0) bulk_wait_all();    // shared memory must outlive the last bulk store
+    if (bulk_out) bulk_wait_all();                 // shared memory must outlive the last bulk store (every lane: its own groups)
 
     if (active) {
         st.t[env] = t; st.episode[env] = (int)episode; st.ep_ret[env] = ep_ret;
