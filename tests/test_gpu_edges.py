@@ -155,3 +155,36 @@ def test_node_nothing_ships_to_observes_zeros_not_nan(mode):
         # obs layout: R*P demands, then per node [stock, bucket(t+1), bucket(rest)]; WholeSaler1 is node 4
         base = env.flat.n_retailers * env.flat.P + 4 * 3
         assert bool((o[:, :, base + 1:base + 3] == -1).all())
+
+
+@pytest.mark.parametrize("env_id,kw", [("supplychain-ntom-v0", {}), ("supplychain-linear-v0", {}), ("supplychain-v0", {}),
+                                       ("supplychain-ntom-v0", dict(nodes_per_echelon=[5, 4, 7, 10]))])
+@pytest.mark.parametrize("mode", ["mixed", "fast_f32"])
+@pytest.mark.parametrize("n", [32 * 5 + 7, 32 * 5 + 8])
+def test_bulk_copy_pipeline_edges(env_id, kw, mode, n):
+    """The action-tile pipeline of the rollout kernels (one or two tiles per warp, requests issued by an elected lane): a rollout of
+    1, 2, 3 or 7 periods, with and without the observation output, and a batch whose last warp is ragged, all agree with the
+    same periods taken through step()."""
+    # the last warp is ragged; with 167 envs some shapes lose the 16-byte alignment the bulk copies need (plain warp copies instead)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    ref = gsc.make(env_id, num_envs=n, mode=mode, seed=4, auto_reset=True, **kw)
+    ref.reset()
+    acts = torch.empty((13, n, ref.n_actions), device="cuda").uniform_(-1, 1, generator=g)
+    want_o, want_r = [], []
+    for t in range(13):
+        o, r, d, _ = ref.step(acts[t])
+        want_o.append(o.clone()); want_r.append(r.clone())
+    want_o, want_r = torch.stack(want_o), torch.stack(want_r)
+    for write_obs in (True, False):
+        env = gsc.make(env_id, num_envs=n, mode=mode, seed=4, auto_reset=True, **kw)
+        env.reset()
+        t0 = 0
+        for T in (1, 2, 3, 7):
+            o, r, d = env.rollout(T, acts[t0:t0 + T].contiguous(), write_obs=write_obs)
+            assert torch.equal(r, want_r[t0:t0 + T]), (write_obs, T)
+            if write_obs:
+                assert torch.equal(o, want_o[t0:t0 + T]), T
+            else:
+                assert o is None
+            t0 += T
+        env.check()                                             # no device-side flag was raised
