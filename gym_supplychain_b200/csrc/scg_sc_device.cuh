@@ -57,6 +57,8 @@ struct ScDevSpec {
     const Real* iamt;       // [n_init]
     const unsigned long long* lt_thr;   // [maxL] stochastic lead times: lt = 1 + #{j < maxL-1 : word >= lt_thr[j]}
     const float *inv_cap, *inv_ms;      // [N*P] 1/stock_capacity, 1/max_ship (0 where max_ship == 0): fp32 obs of the split kernel
+    const double *q_scale, *q_inv;      // [N*P] fixed-point ring of the fp64-state split kernel: slot = amount * q_scale (a power of two)
+    const float* inv_ms_q;              // [N*P] q_inv / max_ship: fp32 obs straight from a fixed-point slot
     const int* dkind;       // [P]
     const double *dlo, *dhi, *dstd, *dpeaks, *dminavg, *dmaxavg;   // [P]
 };

@@ -92,6 +92,14 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
         inv_ms[i] = hs.max_ship[i] > 0 ? (float)(1.0 / hs.max_ship[i]) : 0.0f;
     }
     size_t o_icap = put(inv_cap.data(), inv_cap.size() * sizeof(float)), o_ims = put(inv_ms.data(), inv_ms.size() * sizeof(float));
+    const std::vector<double> q_scale = sc_ring_scales(hs);
+    std::vector<double> q_inv(q_scale.size());
+    std::vector<float> inv_ms_q(q_scale.size());
+    for (size_t i = 0; i < q_scale.size(); ++i) {
+        q_inv[i] = 1.0 / q_scale[i];
+        inv_ms_q[i] = hs.max_ship[i] > 0 ? (float)(q_inv[i] / hs.max_ship[i]) : 0.0f;
+    }
+    size_t o_qs = put_dbl(q_scale), o_qi = put_dbl(q_inv), o_imq = put(inv_ms_q.data(), inv_ms_q.size() * sizeof(float));
 
     unsigned char* d = nullptr;
     SCG_CUDA(cudaMalloc(&d, buf.size()));
@@ -113,6 +121,7 @@ static int sc_build_devspec_t(const ScHostSpec& hs, void** blob_out, void* devsp
     sp.dminavg = SCG_P(double, o_dmin); sp.dmaxavg = SCG_P(double, o_dmax);
     sp.lt_thr = SCG_P(unsigned long long, o_thr);
     sp.inv_cap = SCG_P(float, o_icap); sp.inv_ms = SCG_P(float, o_ims);
+    sp.q_scale = SCG_P(double, o_qs); sp.q_inv = SCG_P(double, o_qi); sp.inv_ms_q = SCG_P(float, o_imq);
 #undef SCG_P
     memcpy(devspec_out, &sp, sizeof(sp));
     *blob_out = d;
