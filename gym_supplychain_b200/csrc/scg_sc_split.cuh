@@ -33,12 +33,23 @@ struct SplitShape {
 // Per-lane registers: the owned nodes of all four echelons, echelon-major, plus the partial sums of what this lane's nodes
 // send to each node of the next echelon (one echelon at a time).  ONE plain struct of arrays, so that every element is a
 // register after unrolling; the per-echelon Pipe policies below are method-only views of it.
-template <class Real, int KT, int P, int L, int MAXPART>
+// fp64 state (mixed mode): the ring is 32-bit fixed point exactly as in RingFixed (scg_sc_static.cuh) -- per (node, product)
+// power-of-two scales from the host (ScDevSpec::q_scale / q_inv = sc_ring_scales), stocks stay fp64.  Half the ring registers
+// of a kernel that otherwise sits at the 255-register limit, 32-bit shuffles for the cross-lane sums.
+template <class Real> struct SplitSlot { using type = Real; static constexpr bool kFixed = false; };
+#if SCG_FIXED_RING
+template <> struct SplitSlot<double> { using type = unsigned; static constexpr bool kFixed = true; };
+#endif
+
+template <class Real, int KT, int P, int L, int MAXPART, int KOWN = 1>
 struct SplitRegs {
+    using Slot = typename SplitSlot<Real>::type;
+    static constexpr bool kFixed = SplitSlot<Real>::kFixed;
     Real stock[KT * P];
-    Real slot[KT * P * L];
+    Slot slot[KT * P * L];
     Real part[MAXPART];
     bool has[MAXPART];                     // compile-time after unrolling: the first push is an assignment
+    Real own[KOWN * P];                    // fixed-point ring: what the lane's suppliers ordered this period (booked after the step)
 };
 
 // Topo policy of ONE echelon as seen by one lane (sc_step_nodes iterates its K owned slots).
@@ -104,19 +115,27 @@ struct SplitTopo {
 
 // Pipe policy of one echelon: a view of the lane's registers (arrivals are applied before the echelons act) -- no data
 // of its own, so the kernel may look at its SplitRegs through it.
-template <class Real, int OFF, int P, int L, int NEXT, int KT, int MAXPART>
-struct SplitPipe : SplitRegs<Real, KT, P, L, MAXPART> {
+template <class Real, int OFF, int P, int L, int NEXT, int KT, int MAXPART, int KOWN>
+struct SplitPipe : SplitRegs<Real, KT, P, L, MAXPART, KOWN> {
+    using Base = SplitRegs<Real, KT, P, L, MAXPART, KOWN>;
     static constexpr bool kTwoPhase = false;
     static constexpr bool kExactObs = false;
     static constexpr int NPART = NEXT * P;
     __device__ __forceinline__ void begin() {
 #pragma unroll
         for (int i = 0; i < MAXPART; ++i) { this->part[i] = (Real)0; this->has[i] = false; }
+        if constexpr (Base::kFixed && OFF == 0) {
+#pragma unroll
+            for (int i = 0; i < KOWN * P; ++i) this->own[i] = (Real)0;
+        }
     }
     __device__ __forceinline__ Real get_stock(int np) const { return this->stock[OFF * P + np]; }
     __device__ __forceinline__ void set_stock(int np, Real v) { this->stock[OFF * P + np] = v; }
     __device__ __forceinline__ Real arrive(int, int) const { return (Real)0; }
-    __device__ __forceinline__ void push_own(int np, int, int, Real amount) { this->slot[(OFF * P + np) * L + L - 1] += amount; }
+    __device__ __forceinline__ void push_own(int np, int, int, Real amount) {
+        if constexpr (Base::kFixed) this->own[np] = amount;          // suppliers only (OFF == 0): np < KOWN * P
+        else this->slot[(OFF * P + np) * L + L - 1] += amount;
+    }
     __device__ __forceinline__ void push(int idx, int, int, Real amount) {
         this->part[idx] = this->has[idx] ? this->part[idx] + amount : amount;
         this->has[idx] = true;
@@ -159,9 +178,10 @@ __device__ __forceinline__ int split_gnode(int e, int l, int q) {       // globa
 }
 
 // The lane's registers from the state arrays in HBM (FROM_SPEC = false) or from the spec's initial state (reset, :402-412).
-template <class Real, int S, int F, int W, int R, int P, int L, int G, bool FROM_SPEC, int KT, int MAXPART>
-__device__ __forceinline__ void split_load_state(const ScDevSpec<Real>& sp, const ScState<Real>& st, SplitRegs<Real, KT, P, L, MAXPART>& rg, int q,
+template <class Real, int S, int F, int W, int R, int P, int L, int G, bool FROM_SPEC, int KT, int MAXPART, int KOWN>
+__device__ __forceinline__ void split_load_state(const ScDevSpec<Real>& sp, const ScState<Real>& st, SplitRegs<Real, KT, P, L, MAXPART, KOWN>& rg, int q,
                                                  long long n, long long env, bool active) {
+    constexpr bool kFixed = SplitRegs<Real, KT, P, L, MAXPART, KOWN>::kFixed;
     using Sh = SplitShape<S, F, W, R>;
     constexpr int KS = (S + G - 1) / G, KF = (F + G - 1) / G, KW = (W + G - 1) / G, KR = (R + G - 1) / G;
     static_assert(KT == KS + KF + KW + KR, "register layout");
@@ -175,20 +195,28 @@ __device__ __forceinline__ void split_load_state(const ScDevSpec<Real>& sp, cons
             for (int p = 0; p < P; ++p) if (l < kcnt[e]) {
                 const int li = (koff[e] + l) * P + p, np = split_gnode<S, F, W, R, G>(e, l, q) * P + p;
                 const bool ok = (q + G * l < Sh::cnt(e)) && active;
+                Real qs = (Real)1;
+                if constexpr (kFixed) qs = (Real)__ldg(sp.q_scale + np);
+                Real tmp[L];                                              // the slots in Real, converted below
                 if constexpr (FROM_SPEC) {
                     rg.stock[li] = ok ? __ldg(sp.stock0 + np) : (Real)0;
 #pragma unroll
-                    for (int k = 0; k < L; ++k) rg.slot[li * L + k] = (Real)0;
+                    for (int k = 0; k < L; ++k) tmp[k] = (Real)0;
                     const int i0 = ok ? sp.ibeg[np] : 0, i1 = ok ? sp.ibeg[np + 1] : 0;
                     for (int i = i0; i < i1; ++i) {                       // initial in-transit material (:405-412)
                         const int when = sp.itime[i] - 1; const Real amt = sp.iamt[i];
 #pragma unroll
-                        for (int k = 0; k < L; ++k) rg.slot[li * L + k] += (when == k) ? amt : (Real)0;
+                        for (int k = 0; k < L; ++k) tmp[k] += (when == k) ? amt : (Real)0;
                     }
                 } else {
                     rg.stock[li] = ok ? st.stock[(long long)np * n + env] : (Real)0;
 #pragma unroll
-                    for (int k = 0; k < L; ++k) rg.slot[li * L + k] = ok ? st.slot[((long long)np * L + k) * n + env] : (Real)0;
+                    for (int k = 0; k < L; ++k) tmp[k] = ok ? st.slot[((long long)np * L + k) * n + env] : (Real)0;
+                }
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    if constexpr (kFixed) rg.slot[li * L + k] = __double2uint_rn(tmp[k] * qs);
+                    else rg.slot[li * L + k] = tmp[k];
                 }
             }
 }
@@ -255,7 +283,9 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 
     const T0 tp0(sp, q); const T1 tp1(sp, q); const T2 tp2(sp, q); const T3 tp3(sp, q);
     constexpr int MAXPART = P * (F > W ? (F > R ? F : R) : (W > R ? W : R));
-    SplitRegs<Real, KT, P, L, MAXPART> rg;
+    using Regs = SplitRegs<Real, KT, P, L, MAXPART, KS>;
+    constexpr bool kFixed = Regs::kFixed;          // fp64 state: the ring as 32-bit fixed point
+    Regs rg;
     SplitDemand<KR, P> dm;
     int t = 0; unsigned episode = 0; double ep_ret = 0.0;
     const unsigned long long genv = (unsigned long long)(in.first_env + env);
@@ -318,12 +348,27 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 #pragma unroll
             for (int i = 0; i < KR * P; ++i) dm.cur_[i] = dm.next_[i];
             // all arrivals first (pushes carry time >= t+1: no same-period dependence), :220-228
+            if constexpr (!kFixed) {
 #pragma unroll
-            for (int i = 0; i < KT * P; ++i) {
-                rg.stock[i] += rg.slot[i * L];
+                for (int i = 0; i < KT * P; ++i) {
+                    rg.stock[i] += rg.slot[i * L];
 #pragma unroll
-                for (int k = 0; k + 1 < L; ++k) rg.slot[i * L + k] = rg.slot[i * L + k + 1];
-                rg.slot[i * L + L - 1] = (Real)0;
+                    for (int k = 0; k + 1 < L; ++k) rg.slot[i * L + k] = rg.slot[i * L + k + 1];
+                    rg.slot[i * L + L - 1] = (Real)0;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int l = 0; l < KMAX; ++l)
+#pragma unroll
+                        for (int p = 0; p < P; ++p) if (l < kcnt[e]) {
+                            const int i = (koff[e] + l) * P + p;
+                            rg.stock[i] = fma((double)rg.slot[i * L], __ldg(sp.q_inv + gnode(e, l) * P + p), rg.stock[i]);
+#pragma unroll
+                            for (int k = 0; k + 1 < L; ++k) rg.slot[i * L + k] = rg.slot[i * L + k + 1];
+                            rg.slot[i * L + L - 1] = 0u;
+                        }
             }
         }
         SplitActions<Real, Io> ar{s_act + e_in_warp * A, RANDOM_ACT, in.key, genv, episode, t, Philox4{0, 0, 0, 0}, -1};
@@ -331,43 +376,71 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
         // echelon by echelon: the lane's nodes act, the partial shipments are summed over the env's lanes (all lanes of the
         // warp take part in the shuffles) and each destination's owner books the total into its ring
         {
-            auto& pp = static_cast<SplitPipe<Real, koff[0], P, L, F, KT, MAXPART>&>(rg);
+            auto& pp = static_cast<SplitPipe<Real, koff[0], P, L, F, KT, MAXPART, KS>&>(rg);
             pp.begin();
             if (stepping) cost += sc_step_nodes<Real>(tp0, pp, t, ar, lr, dm);
+            if constexpr (kFixed) if (stepping) {  // what the lane's suppliers ordered: one rounding per (node, product)
+#pragma unroll
+                for (int l = 0; l < KS; ++l)
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        rg.slot[(l * P + p) * L + L - 1] = __double2uint_rn(rg.own[l * P + p] * __ldg(sp.q_scale + gnode(0, l) * P + p));
+            }
 #pragma unroll
             for (int i = 0; i < F; ++i)
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const Real tot = group_sum<G>(pp.part[i * P + p]);
-                    rg.slot[((koff[1] + i / G) * P + p) * L + L - 1] += (q == i % G) ? tot : (Real)0;
+                    const int tail = ((koff[1] + i / G) * P + p) * L + L - 1;
+                    if constexpr (kFixed) {
+                        // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
+                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(1) + i) * P + p)));
+                        rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
+                    } else {
+                        const Real tot = group_sum<G>(pp.part[i * P + p]);
+                        rg.slot[tail] += (q == i % G) ? tot : (Real)0;
+                    }
                 }
         }
         {
-            auto& pp = static_cast<SplitPipe<Real, koff[1], P, L, W, KT, MAXPART>&>(rg);
+            auto& pp = static_cast<SplitPipe<Real, koff[1], P, L, W, KT, MAXPART, KS>&>(rg);
             pp.begin();
             if (stepping) cost += sc_step_nodes<Real>(tp1, pp, t, ar, lr, dm);
 #pragma unroll
             for (int i = 0; i < W; ++i)
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const Real tot = group_sum<G>(pp.part[i * P + p]);
-                    rg.slot[((koff[2] + i / G) * P + p) * L + L - 1] += (q == i % G) ? tot : (Real)0;
+                    const int tail = ((koff[2] + i / G) * P + p) * L + L - 1;
+                    if constexpr (kFixed) {
+                        // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
+                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(2) + i) * P + p)));
+                        rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
+                    } else {
+                        const Real tot = group_sum<G>(pp.part[i * P + p]);
+                        rg.slot[tail] += (q == i % G) ? tot : (Real)0;
+                    }
                 }
         }
         {
-            auto& pp = static_cast<SplitPipe<Real, koff[2], P, L, R, KT, MAXPART>&>(rg);
+            auto& pp = static_cast<SplitPipe<Real, koff[2], P, L, R, KT, MAXPART, KS>&>(rg);
             pp.begin();
             if (stepping) cost += sc_step_nodes<Real>(tp2, pp, t, ar, lr, dm);
 #pragma unroll
             for (int i = 0; i < R; ++i)
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const Real tot = group_sum<G>(pp.part[i * P + p]);
-                    rg.slot[((koff[3] + i / G) * P + p) * L + L - 1] += (q == i % G) ? tot : (Real)0;
+                    const int tail = ((koff[3] + i / G) * P + p) * L + L - 1;
+                    if constexpr (kFixed) {
+                        // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
+                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(3) + i) * P + p)));
+                        rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
+                    } else {
+                        const Real tot = group_sum<G>(pp.part[i * P + p]);
+                        rg.slot[tail] += (q == i % G) ? tot : (Real)0;
+                    }
                 }
         }
         {
-            auto& pp = static_cast<SplitPipe<Real, koff[3], P, L, 0, KT, MAXPART>&>(rg);
+            auto& pp = static_cast<SplitPipe<Real, koff[3], P, L, 0, KT, MAXPART, KS>&>(rg);
             pp.begin();
             if (stepping) cost += sc_step_nodes<Real>(tp3, pp, t, ar, lr, dm);
         }
@@ -418,7 +491,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                             for (int p = 0; p < P; ++p) {
                                 const int li = (koff[e] + l) * P + p;
                                 o[p] = unit((float)rg.stock[li], __ldg(sp.inv_cap + nd * P + p));
-                                const float ims = __ldg(sp.inv_ms + nd * P + p);
+                                const float ims = kFixed ? __ldg(sp.inv_ms_q + nd * P + p) : __ldg(sp.inv_ms + nd * P + p);   // fixed point: quantum folded in
 #pragma unroll
                                 for (int k = 0; k < L; ++k) o[P + p * L + k] = unit((float)rg.slot[li * L + k], ims);   // ring == lead time: last bucket / 1
                             }
@@ -454,7 +527,10 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                         const int li = (koff[e] + l) * P + p, np = gnode(e, l) * P + p;
                         st.stock[(long long)np * n + env] = rg.stock[li];
 #pragma unroll
-                        for (int k = 0; k < L; ++k) st.slot[((long long)np * L + k) * n + env] = rg.slot[li * L + k];
+                        for (int k = 0; k < L; ++k) {
+                            if constexpr (kFixed) st.slot[((long long)np * L + k) * n + env] = (double)rg.slot[li * L + k] * __ldg(sp.q_inv + np);
+                            else st.slot[((long long)np * L + k) * n + env] = rg.slot[li * L + k];
+                        }
                     }
     }
     rs.flush(st.stats);
