@@ -364,7 +364,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
 #pragma unroll
                         for (int p = 0; p < P; ++p) if (l < kcnt[e]) {
                             const int i = (koff[e] + l) * P + p;
-                            rg.stock[i] = fma((double)rg.slot[i * L], __ldg(sp.q_inv + gnode(e, l) * P + p), rg.stock[i]);
+                            rg.stock[i] = fma(u2d(rg.slot[i * L]), __ldg(sp.q_inv + gnode(e, l) * P + p), rg.stock[i]);
 #pragma unroll
                             for (int k = 0; k + 1 < L; ++k) rg.slot[i * L + k] = rg.slot[i * L + k + 1];
                             rg.slot[i * L + L - 1] = 0u;
@@ -393,7 +393,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                     const int tail = ((koff[1] + i / G) * P + p) * L + L - 1;
                     if constexpr (kFixed) {
                         // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
-                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(1) + i) * P + p)));
+                        const unsigned tot = group_sum<G>(d2u_wrap(pp.part[i * P + p], __ldg(sp.q_scale + (Sh::base(1) + i) * P + p)));
                         rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
                     } else {
                         const Real tot = group_sum<G>(pp.part[i * P + p]);
@@ -412,7 +412,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                     const int tail = ((koff[2] + i / G) * P + p) * L + L - 1;
                     if constexpr (kFixed) {
                         // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
-                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(2) + i) * P + p)));
+                        const unsigned tot = group_sum<G>(d2u_wrap(pp.part[i * P + p], __ldg(sp.q_scale + (Sh::base(2) + i) * P + p)));
                         rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
                     } else {
                         const Real tot = group_sum<G>(pp.part[i * P + p]);
@@ -431,7 +431,7 @@ sc_split_rollout(ScDevSpec<Real> sp, ScState<Real> st, ScInputs in, int n_steps,
                     const int tail = ((koff[3] + i / G) * P + p) * L + L - 1;
                     if constexpr (kFixed) {
                         // each lane's partial in units of the DESTINATION's quantum, summed as integers (order-independent)
-                        const unsigned tot = group_sum<G>(__double2uint_rn(pp.part[i * P + p] * __ldg(sp.q_scale + (Sh::base(3) + i) * P + p)));
+                        const unsigned tot = group_sum<G>(d2u_wrap(pp.part[i * P + p], __ldg(sp.q_scale + (Sh::base(3) + i) * P + p)));
                         rg.slot[tail] = (stepping && q == i % G) ? tot : rg.slot[tail];     // a frozen env keeps its ring
                     } else {
                         const Real tot = group_sum<G>(pp.part[i * P + p]);

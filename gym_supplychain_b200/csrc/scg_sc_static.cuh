@@ -291,7 +291,14 @@ struct RingRegs {
 // the observation reads the slot with an ALU int->float conversion instead of an fp64->fp32 one.  This period's pushes
 // are accumulated in fp64 (`acc`, live only between the first and the last source of a destination) and rounded ONCE
 // in commit(); conversions saturate, so an out-of-contract supply action far outside [-1, 1] clips at 8x capacity.
-template <int NP, int L>
+// uint <-> double through the 2^52 trick: (2^52 + u) is exactly the double whose low word is u, so one DADD / DFMA on the FP64
+// pipe replaces an I2F / F2I on the quarter-rate conversion pipe (the busiest pipe of the fp64-state kernels).  The to-integer
+// direction rounds to nearest-even like cvt.rni but WRAPS instead of saturating: used only where the amount is bounded by a
+// capped stock (shipments); a supplier's own order (bounded only by the action) keeps the saturating conversion.
+__device__ __forceinline__ double u2d(unsigned u) { return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0; }
+__device__ __forceinline__ unsigned d2u_wrap(double x, double scale) { return (unsigned)__double2loint(fma(x, scale, 4503599627370496.0)); }
+
+template <int NP, int L, int NSUP = NP>      // NSUP: the first NSUP (node, product) pairs belong to suppliers
 struct RingFixed {
     static constexpr bool kTwoPhase = true;
     static constexpr bool kExactObs = false;
@@ -307,8 +314,11 @@ struct RingFixed {
     }
     __device__ __forceinline__ double get_stock(int np) const { return stock[np]; }
     __device__ __forceinline__ void set_stock(int np, double v) { stock[np] = v; }
+    // measured (profiles/r2_ring_conversion_2p52_ab.log, bit-identical results): ntom +1.1 %, 2-2-2-2 / 2 products +0.5 %, but the
+    // small chains, which do not wait for the conversion pipe, lose (linear -1.2 %, 1-1-1-3 -0.3 %) -> from 8 (node, product) pairs on
+    static constexpr bool kMagic = NP >= 8;
     __device__ __forceinline__ double arrive(int np, int) {
-        const double a = (double)slot[np * L] * q_inv[np];
+        const double a = (kMagic ? u2d(slot[np * L]) : (double)slot[np * L]) * q_inv[np];
 #pragma unroll
         for (int k = 0; k + 1 < L; ++k) slot[np * L + k] = slot[np * L + k + 1];
         has[np] = false;
@@ -321,15 +331,16 @@ struct RingFixed {
     __device__ __forceinline__ void push_own(int np, int t, int lt, double amount) { push(np, t, lt, amount); }
     __device__ __forceinline__ void commit() {
 #pragma unroll
-        for (int np = 0; np < NP; ++np) slot[np * L + L - 1] = has[np] ? __double2uint_rn(acc[np] * q_scale[np]) : 0u;
+        for (int np = 0; np < NP; ++np)
+            slot[np * L + L - 1] = has[np] ? ((!kMagic || np < NSUP) ? __double2uint_rn(acc[np] * q_scale[np]) : d2u_wrap(acc[np], q_scale[np])) : 0u;
     }
     __device__ __forceinline__ void load_slot(int i, double v) { slot[i] = __double2uint_rn(v * q_scale[i / L]); }
     __device__ __forceinline__ double store_slot(int i) const { return (double)slot[i] * q_inv[i / L]; }
     __device__ __forceinline__ float obs_slot(int i) const { return (float)slot[i]; }     // host folds q_inv into obs_mid / obs_last
 };
 
-template <bool FIXED, class Real, int NP, int L, bool STOCH> struct PipeChoice { using type = RingRegs<Real, NP, L, STOCH>; };
-template <int NP, int L> struct PipeChoice<true, double, NP, L, false> { using type = RingFixed<NP, L>; };
+template <bool FIXED, class Real, int NP, int L, bool STOCH, int NSUP = NP> struct PipeChoice { using type = RingRegs<Real, NP, L, STOCH>; };
+template <int NP, int L, int NSUP> struct PipeChoice<true, double, NP, L, false, NSUP> { using type = RingFixed<NP, L, NSUP>; };
 
 // Reads one env's row of LEN elements out of the warp tile, 16/8/4 bytes at a time.  All
 // indices are compile-time constants after unrolling, so the chunk cache folds away.
@@ -539,7 +550,7 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
 
     // fp64 state with fp32 I/O and a constant lead time: in-transit material as 32-bit fixed point (RingFixed)
     constexpr bool kFixed = (SCG_FIXED_RING != 0) && sizeof(Real) == 8 && sizeof(Io) == 4 && !STOCH;
-    using Pp = typename PipeChoice<kFixed, Real, NP, ML, STOCH>::type;
+    using Pp = typename PipeChoice<kFixed, Real, NP, ML, STOCH, S * P>::type;
     Pp pp(c.q_scale, c.q_inv);
     if constexpr (STOCH) {
         Real* tab = reinterpret_cast<Real*>(smem_raw + 128);
