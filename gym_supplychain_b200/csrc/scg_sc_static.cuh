@@ -315,8 +315,10 @@ struct RingFixed {
     __device__ __forceinline__ double get_stock(int np) const { return stock[np]; }
     __device__ __forceinline__ void set_stock(int np, double v) { stock[np] = v; }
     // measured (profiles/r2_ring_conversion_2p52_ab.log, bit-identical results): ntom +1.1 %, 2-2-2-2 / 2 products +0.5 %, but the
-    // small chains, which do not wait for the conversion pipe, lose (linear -1.2 %, 1-1-1-3 -0.3 %) -> from 8 (node, product) pairs on
-    static constexpr bool kMagic = NP >= 8;
+    // small chains, which do not wait for the conversion pipe, lose (linear -1.2 %, 1-1-1-3 -0.3 %) -> from 8 (node, product) pairs on;
+    // and a chain at the edge of the register file spills more with it (2-3-2-4, 3 products, lead time 3: 165 state registers,
+    // 0.57 -> 0.48, profiles/r2_midsize_chains_v5.log) -> only while stocks + ring stay within 150 registers
+    static constexpr bool kMagic = NP >= 8 && NP * (2 + L) <= 150;
     __device__ __forceinline__ double arrive(int np, int) {
         const double a = (kMagic ? u2d(slot[np * L]) : (double)slot[np * L]) * q_inv[np];
 #pragma unroll
