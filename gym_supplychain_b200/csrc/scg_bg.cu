@@ -18,8 +18,11 @@ namespace scg {
 #ifndef SCG_BG_PF
 #define SCG_BG_PF 2
 #endif
+// Blocks of 256 threads per SM: 3 (80 registers).  At 4 (64 registers) the kernels with a ring of 4 and Philox demand / delays
+// spill -- with the branch-free bookings below 0.455 of the HBM peak instead of 0.643 -- and the others are within 1 % either way
+// (profiles/r2_beergame_onehot_bookings_ab.log, r2_beergame_launch_shape_ab.log).
 #ifndef SCG_BG_MINB
-#define SCG_BG_MINB 4
+#define SCG_BG_MINB 3
 #endif
 constexpr int BG_PF = SCG_BG_PF;
 
@@ -156,24 +159,26 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
                 fill[i] = incoming[i] + back[i];
                 deliver[i] = min(inv[i], fill[i]);
             }
+            // Where this week's shipments land: ONE delay for all levels, so the one-hot of the ring slot (and of "delay 0":
+            // straight into the inventory) is built once per week and every booking is a multiply-add by 1 or 0 -- no branch on
+            // a per-env random delay (lanes of a warp diverged on it), no compare + select per (slot, level).
+            int oh0 = delay == 0 ? 1 : 0, oh[RMAX];
+#pragma unroll
+            for (int k = 0; k < RMAX; ++k) oh[k] = (k == delay - 1) ? 1 : 0;
             // ship downstream; delay 0 lands in the lower level's inventory before its own decrement (:93-96)
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) if (i + 1 < L) {
-                if (delay == 0) inv[i] += deliver[i + 1];
-                else {
+                inv[i] += deliver[i + 1] * oh0;
 #pragma unroll
-                    for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] += (k == delay - 1) ? deliver[i + 1] : 0;
-                }
+                for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][i] += deliver[i + 1] * oh[k];
             }
             // 3. inventory / backlog (:101-103)
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) if (i < L) { inv[i] -= deliver[i]; back[i] = fill[i] - deliver[i]; }
             // 4. the brewery's own order comes back after the delay (:111-114)
-            if (delay == 0) inv[L - 1] += placed[L - 1];
-            else {
+            inv[L - 1] += placed[L - 1] * oh0;
 #pragma unroll
-                for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][L - 1] += (k == delay - 1) ? placed[L - 1] : 0;
-            }
+            for (int k = 0; k < RMAX; ++k) if (k < RING) tr[k][L - 1] += placed[L - 1] * oh[k];
             // 5. place orders (beergame_env.py:121 / beergame2_env.py:168)
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) if (i < L) placed[i] = v2 ? act[i] : incoming[i] + act[i];
