@@ -186,7 +186,7 @@ void pack_consts(const ScHostSpec& hs, int S, int F, int W, int R, int ML, Packe
         pk.put<Real>("init_slot", init.data(), init.size());
     }
     const std::vector<double> qs = sc_ring_scales(hs);
-    const bool fixed_ring = sizeof(Real) == 8 && !hs.stochL;
+    const bool fixed_ring = sizeof(Real) == 8 && (!hs.stochL || SCG_FIXED_RING_STOCH != 0);
     {
         std::vector<Real> a(NP), b(NP);
         for (int i = 0; i < NP; ++i) { a[i] = (Real)qs[i]; b[i] = (Real)(1.0 / qs[i]); }
@@ -522,7 +522,7 @@ static bool jit_plan(ScJit& j, const ScHostSpec& hs, int mode) {
     size_t tile = (size_t)32 * (hs.A + hs.O) * es;
     const size_t budget = (size_t)227 * 1024 - 128 - 1024;
     // state registers: fp32 stocks + ring; fp64 stocks + 32-bit fixed-point ring (mixed, constant lead time); else all fp64
-    const bool fixed_ring = f64 && es == 4 && !hs.stochL;
+    const bool fixed_ring = f64 && es == 4 && (!hs.stochL || SCG_FIXED_RING_STOCH != 0);
     const int state_regs = fixed_ring ? np_all * 2 + np_all * j.ML : np_all * (1 + j.ML) * (f64 ? 2 : 1);
     int regs = (state_regs + 88 + 7) / 8 * 8;
     // an fp64-state kernel beyond 168 registers wants the whole file: it lives on instruction-level parallelism

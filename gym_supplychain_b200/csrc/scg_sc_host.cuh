@@ -50,6 +50,7 @@ static inline std::vector<double> sc_ring_scales(const ScHostSpec& hs) {
         double init = 0.0;
         for (int k = hs.ibeg[np]; k < hs.ibeg[np + 1]; ++k) init += std::fabs(hs.iamt[k]);
         if (2.0 * init > bound[np]) bound[np] = 2.0 * init;
+        if (hs.stochL) bound[np] *= (double)hs.maxL;        // stochastic lead times: one arrival slot collects up to maxL periods' pushes
         int k = 0;
         if (bound[np] > 0 && std::isfinite(bound[np])) k = std::ilogb(4294967295.0 / bound[np]);
         k = k < -60 ? -60 : (k > 60 ? 60 : k);
@@ -159,7 +160,7 @@ template <class Real, int S, int F, int W, int R, int P, int L, int ML, bool STO
 static void sc_fill_consts(const ScHostSpec& hs, LayeredConsts<Real, S, F, W, R, P, L, ML, STOCH>& c) {
     memset(&c, 0, sizeof(c));
     constexpr int N = S + F + W + R, NP = N * P, E = S * F + F * W + W * R;
-    constexpr bool fixed_ring = sizeof(Real) == 8 && !STOCH;       // RingFixed: the fp32-I/O kernel reads obs_mid / obs_last
+    constexpr bool fixed_ring = sizeof(Real) == 8 && (!STOCH || SCG_FIXED_RING_STOCH != 0);   // RingFixed*: the fp32-I/O kernel reads obs_mid / obs_last
     const std::vector<double> qs = sc_ring_scales(hs);
     for (int i = 0; i < NP; ++i) {
         c.cap[i] = (Real)hs.cap[i]; c.hold[i] = (Real)hs.hold[i]; c.stock0[i] = (Real)hs.stock0[i];

@@ -14,6 +14,9 @@
 #define SCG_V2_MINB_F64 4
 #endif
 
+#ifndef SCG_V6_MINB_F64
+#define SCG_V6_MINB_F64 3
+#endif
 #ifndef SCG_V3_THREADS_F64
 #define SCG_V3_THREADS_F64 64
 #endif
@@ -52,7 +55,7 @@ int sc_run_mixed(const ScRun& r) {
             case 3: return sc_launch_layered<double, float, 3, 3, 3, 3, 2, 2, SCG_SHAPE1(SCG_V3_THREADS_F64, SCG_V3_MINB_F64)>(r);
             case 4: return sc_launch_layered<double, float, 1, 1, 1, 3, 1, 2, SCG_SHAPE1(128, 3)>(r);
             case 5: return sc_launch_layered<double, float, 2, 2, 2, 2, 2, 2, SCG_SHAPE1(64, 4)>(r);
-            case 6: return sc_launch_layered<double, float, 2, 2, 2, 2, 1, 2, SCG_SHAPE1(128, 3), 4, true>(r);
+            case 6: return sc_launch_layered<double, float, 2, 2, 2, 2, 1, 2, SCG_SHAPE1(128, SCG_V6_MINB_F64), 4, true>(r);
             default: break;
         }
     }

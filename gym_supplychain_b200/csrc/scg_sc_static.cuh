@@ -341,8 +341,50 @@ struct RingFixed {
     __device__ __forceinline__ float obs_slot(int i) const { return (float)slot[i]; }     // host folds q_inv into obs_mid / obs_last
 };
 
+// The same fixed-point ring for STOCHASTIC lead times (L = max lead time slots).  A push lands in a data-dependent slot, so it
+// cannot wait for a per-period commit: each amount is rounded to the (node, product) quantum when it is pushed and booked with one
+// integer multiply-add per slot against a row of an L x L 0/1 table in shared memory (the integer twin of RingRegs::push).  The
+// host leaves log2(L) bits of headroom in the scale (sc_ring_scales): a slot can collect the pushes of up to L periods.
+template <int NP, int L, int NSUP = NP>
+struct RingFixedStoch {
+    static constexpr bool kTwoPhase = true;
+    static constexpr bool kExactObs = false;
+    static constexpr bool kFixed = true;
+    double stock[NP];
+    unsigned slot[NP * L];
+    const double* q_scale; const double* q_inv;
+    const unsigned* onehot = nullptr;  // L x L identity in shared memory, row lt-1 = where a lead time lt lands
+    __device__ __forceinline__ RingFixedStoch(const double* qs, const double* qi) : q_scale(qs), q_inv(qi) {}
+    __device__ __forceinline__ void commit() {}
+    __device__ __forceinline__ double get_stock(int np) const { return stock[np]; }
+    __device__ __forceinline__ void set_stock(int np, double v) { stock[np] = v; }
+    __device__ __forceinline__ double arrive(int np, int) {
+        const double a = (double)slot[np * L] * q_inv[np];
+#pragma unroll
+        for (int k = 0; k + 1 < L; ++k) slot[np * L + k] = slot[np * L + k + 1];
+        slot[np * L + L - 1] = 0u;
+        return a;
+    }
+    __device__ __forceinline__ void push(int np, int, int lt, double amount) {
+        const unsigned q = __double2uint_rn(amount * q_scale[np]);
+        const unsigned* row = onehot + (lt - 1) * L;
+#pragma unroll
+        for (int k = 0; k < L; ++k) slot[np * L + k] += q * row[k];
+    }
+    __device__ __forceinline__ void push_own(int np, int t, int lt, double amount) { push(np, t, lt, amount); }
+    __device__ __forceinline__ void load_slot(int i, double v) { slot[i] = __double2uint_rn(v * q_scale[i / L]); }
+    __device__ __forceinline__ double store_slot(int i) const { return (double)slot[i] * q_inv[i / L]; }
+    __device__ __forceinline__ float obs_slot(int i) const { return (float)slot[i]; }
+};
+
+template <bool C, class A, class B> struct TypeIf { using type = A; };           // (no <type_traits> under NVRTC)
+template <class A, class B> struct TypeIf<false, A, B> { using type = B; };
+#ifndef SCG_FIXED_RING_STOCH
+#define SCG_FIXED_RING_STOCH 1  // mixed mode, stochastic lead times: RingFixedStoch (0 = the fp64 ring)
+#endif
 template <bool FIXED, class Real, int NP, int L, bool STOCH, int NSUP = NP> struct PipeChoice { using type = RingRegs<Real, NP, L, STOCH>; };
 template <int NP, int L, int NSUP> struct PipeChoice<true, double, NP, L, false, NSUP> { using type = RingFixed<NP, L, NSUP>; };
+template <int NP, int L, int NSUP> struct PipeChoice<true, double, NP, L, true, NSUP> { using type = RingFixedStoch<NP, L, NSUP>; };
 
 // Reads one env's row of LEN elements out of the warp tile, 16/8/4 bytes at a time.  All
 // indices are compile-time constants after unrolling, so the chunk cache folds away.
@@ -551,12 +593,13 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     __syncwarp();
 
     // fp64 state with fp32 I/O and a constant lead time: in-transit material as 32-bit fixed point (RingFixed)
-    constexpr bool kFixed = (SCG_FIXED_RING != 0) && sizeof(Real) == 8 && sizeof(Io) == 4 && !STOCH;
+    constexpr bool kFixed = (SCG_FIXED_RING != 0) && sizeof(Real) == 8 && sizeof(Io) == 4 && (!STOCH || SCG_FIXED_RING_STOCH != 0);
     using Pp = typename PipeChoice<kFixed, Real, NP, ML, STOCH, S * P>::type;
     Pp pp(c.q_scale, c.q_inv);
     if constexpr (STOCH) {
-        Real* tab = reinterpret_cast<Real*>(smem_raw + 128);
-        for (int i = threadIdx.x; i < ML * ML; i += THREADS) tab[i] = (i / ML == i % ML) ? (Real)1 : (Real)0;
+        using Tab = typename TypeIf<kFixed, unsigned, Real>::type;                 // the header is sized for Real: enough for both
+        Tab* tab = reinterpret_cast<Tab*>(smem_raw + 128);
+        for (int i = threadIdx.x; i < ML * ML; i += THREADS) tab[i] = (i / ML == i % ML) ? (Tab)1 : (Tab)0;
         __syncthreads();
         pp.onehot = tab;
     }
@@ -727,7 +770,10 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
                             else ow.put(o++, unit(pp.obs_slot(np * ML + k), c.obs_mid[np]));
                         }
                         if constexpr (kFixed) {
-                            ow.put(o++, unit(pp.obs_slot(np * ML + L - 1), c.obs_last[np]));     // ML == L: one slot
+                            unsigned rest = 0u;                    // everything arriving at t+L or later: an exact integer sum
+#pragma unroll
+                            for (int k = L - 1; k < ML; ++k) rest += pp.slot[np * ML + k];
+                            ow.put(o++, unit((float)rest, c.obs_last[np]));
                         } else {
                             Real rest = (Real)0;                   // everything arriving at t+L or later
 #pragma unroll
