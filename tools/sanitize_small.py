@@ -20,6 +20,22 @@ for env_id in ("supplychain-linear-v0", "supplychain-2perstage-v0", "supplychain
             env.reset(torch.ones(n, dtype=torch.uint8, device="cuda"))
             assert torch.isfinite(r).all() and int(d.sum()) == n
             del env
+for mode in ("fast_f32", "mixed"):                              # node-parallel kernel (two action tiles with fp64 state), ragged batches
+    for n in (3, 45):
+        env = gsc.make("supplychain-ntom-v0", num_envs=n, mode=mode, seed=1, auto_reset=True, total_time_steps=5, nodes_per_echelon=[5, 4, 7, 10])
+        env.reset()
+        a = (torch.rand(7, n, env.n_actions, device="cuda") * 2 - 1)
+        o, r, d = env.rollout(7, a)
+        env.rollout(4, a[:4].contiguous(), write_obs=False)
+        assert torch.isfinite(r).all() and env.scg_info.kernel_variant == 101
+        del env
+for n in (40, 64):                                               # two-tile pipeline without the observation output
+    env = gsc.make("supplychain-ntom-v0", num_envs=n, mode="mixed", seed=1, auto_reset=True, total_time_steps=6)
+    env.reset()
+    a = (torch.rand(5, n, env.n_actions, device="cuda") * 2 - 1)
+    for T in (1, 2, 5):
+        env.rollout(T, a[:T].contiguous(), write_obs=False)
+    del env
 gen = gsc.make("supplychain-ntom-v0", num_envs=65, mode="fast_f32", force_generic=True, build_info=True)
 gen.reset(); gen.rollout(4)
 for n in (1, 33, 300):
