@@ -24,7 +24,9 @@ namespace scg {
 #ifndef SCG_BG_MINB
 #define SCG_BG_MINB 3
 #endif
-constexpr int BG_PF = SCG_BG_PF;
+#ifndef SCG_BG_PF_TABLE
+#define SCG_BG_PF_TABLE 3       // kernels whose demand / delays come from the spec's tables: registers to spare at 80 per thread
+#endif
 
 // VER: -1 = the game version is read at run time, 0 / 2 = known (beergame-v0 / -v2).
 // INP:  0 = where demand / delay come from is decided at run time (injected tables, Philox, the spec's tables, any mix),
@@ -203,6 +205,9 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
         if (pipelined) {
             // groups of BG_PF weeks, double-buffered: the rows of group g+1 are requested before group g is computed
             // and only copied into `cur` afterwards, so BG_PF independent 16-byte loads per lane stay in flight
+            // depth: 3 weeks for the table-driven kernels (v2 0.684 -> 0.708, v0 0.700 -> 0.709 of the HBM peak), 2 where Philox
+            // demand / delays need the registers (3 costs them 6 %, 4 spills everywhere; profiles/r2_beergame_prefetch_depth_ab.log)
+            constexpr int BG_PF = INP == 1 ? SCG_BG_PF_TABLE : SCG_BG_PF;
             int4 cur[BG_PF], nxt[BG_PF];
 #pragma unroll
             for (int u = 0; u < BG_PF; ++u) {
