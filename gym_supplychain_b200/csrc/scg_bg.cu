@@ -24,6 +24,9 @@ namespace scg {
 #ifndef SCG_BG_MINB
 #define SCG_BG_MINB 3
 #endif
+#ifndef SCG_BG_THREADS
+#define SCG_BG_THREADS 256
+#endif
 #ifndef SCG_BG_PF_TABLE
 #define SCG_BG_PF_TABLE 3       // kernels whose demand / delays come from the spec's tables: registers to spare at 80 per thread
 #endif
@@ -34,7 +37,7 @@ namespace scg {
 //       (customer_demand=(lo,hi), shipment_delays=(lo,hi): beergame2_env.py:86-92).  The specialisations drop ~30 uniform
 //       tests and branches per week from a kernel that moves only 37 bytes per env-week.
 template <int LMAX, int RMAX, bool STATIC, int VER, int INP>
-__global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand_,
+__global__ void __launch_bounds__(SCG_BG_THREADS, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDevSpec sp, BgState st, const int32_t* __restrict__ inj_demand_,
                                                  const int32_t* __restrict__ inj_delays_, RngKey key, long long first_env,
                                                  int auto_reset, int n_steps, const unsigned char* __restrict__ reset_mask,
                                                  int do_reset, const int32_t* __restrict__ actions, int32_t* __restrict__ obs,
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(256, STATIC ? SCG_BG_MINB : 1) bg_kernel(BgDev
 }
 
 int bg_run(const BgRun& r) {
-    const int threads = 256;
+    const int threads = SCG_BG_THREADS;
     const unsigned blocks = (unsigned)((r.st.n + threads - 1) / threads);
     const int do_reset = r.op == SC_OP_RESET ? 1 : 0;
     const int n_steps = r.op == SC_OP_RESET ? 0 : r.n_steps;
