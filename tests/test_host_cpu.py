@@ -219,7 +219,10 @@ def test_negative_ship_capacity_diagnostic():
 @pytest.mark.parametrize("kw,mode", [
     (dict(nodes_per_echelon=[2, 3, 2, 4], num_products=3, avg_leadtime=3, max_leadtime=3), "mixed"),
     (dict(nodes_per_echelon=[5, 4, 7, 10]), "fast_f32"),
+    (dict(nodes_per_echelon=[5, 4, 7, 10]), "mixed"),          # node-parallel kernel, fixed-point ring, two action tiles
+    (dict(nodes_per_echelon=10), "mixed"),                     # node-parallel kernel, 8 lanes per env
     (dict(nodes_per_echelon=4), "mixed"),
+    (dict(nodes_per_echelon=3, num_products=3, stochastic_leadtimes=True, avg_leadtime=2, max_leadtime=4), "mixed"),   # RingFixedStoch
 ])
 def test_instantiated_kernels_keep_the_env_state_in_registers(tmp_path, monkeypatch, kw, mode):
     """A run-time index that survives unrolling silently moves the WHOLE env state to local memory (seen twice while
