@@ -565,9 +565,9 @@ sc_layered_rollout(const __grid_constant__ LayeredConsts<Real, S, F, W, R, P, L,
     // one warp per block: every tile / barrier / bulk-copy address derives from blockIdx alone, so the compiler keeps it in
     // uniform registers (a warp index read from threadIdx costs a register-to-uniform loop around every bulk copy)
     const int lane = threadIdx.x & 31, warp = THREADS == 32 ? 0 : (int)(threadIdx.x >> 5);
-    // smem: [one mbarrier per warp, padded to 128 B][per warp: action tile | obs tile]
+    // smem: [two mbarriers per warp (one per action tile), padded to 128 B][per warp: action tile(s) | obs tile]
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp * 2;     // two per warp (one per action tile)
-    // [128 B: one mbarrier per warp][STOCH: ML x ML one-hot table of Real, padded to 128 B][per warp: action tile | obs tile]
+    // [128 B: the mbarriers][STOCH: ML x ML 0/1 table (Real, or unsigned for the fixed-point ring), padded to 128 B][per warp: action tile(s) | obs tile]
     constexpr int kHdr = layered_smem_header<Real, ML, STOCH>();
     constexpr int kActTiles = layered_action_tiles<Real, Io, NP>();
     Io* s_act0 = reinterpret_cast<Io*>(smem_raw + kHdr) + (size_t)warp * 32 * (kActTiles * A + O);
